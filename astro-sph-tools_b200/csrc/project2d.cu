@@ -1,0 +1,715 @@
+// project2d.cu -- 2-D line-of-sight projection of SPH particles onto a pixel map, sm_100a.
+//
+// Replaces create_image -> process_chunk -> calculate_pixel_value -> kernel_func of the reference
+// (tools/projections/_projector.py:75-120,13-73; _pixel_calculations.pyx:9-36; _kernels.pyx:9-20).
+// The reference gathers: for every pixel it scans every candidate particle.  Here the work is turned
+// round (scatter by particle, gather by screen tile):
+//
+//   K1 bin_kernel        one thread per particle: float64 bbox (ast_geom.h), class, pair count; particles whose
+//                        bbox is a few pixels are deposited right here with float64 atomics (the HBM-bound
+//                        regime: inputs are read exactly once); the others get a 32-byte record.
+//   scan                 exclusive scan of the per-block pair counts.
+//   K3 emit_kernel       writes (tile key << 32 | particle) pairs in emit order.
+//   radix sort           stable, by tile key (scan_sort.cuh).
+//   K5 tile_range_kernel first/last pair of every tile.
+//   K6 tile_accum_kernel one CTA per 32x32-pixel tile, 4 warps each owning a 16x16 sub-tile, 8 pixels per
+//                        thread in registers; particle records are staged through shared memory in
+//                        tile-relative float32 (converted from float64 at staging time); per staged chunk the
+//                        float32 partial sums are folded into float64 accumulators; the tile is written once.
+//                        Particles covering more than huge_min_tiles tiles are not binned: every tile walks the
+//                        (short) global list of them and culls per warp.
+#include <string.h>
+
+#include "ast_geom.h"
+#include "ast_math.h"
+#include "common.cuh"
+#include "scan_sort.cuh"
+
+namespace ast {
+
+constexpr int TILE = AST_TILE;
+constexpr int kBinThreads = 256;
+constexpr int kMaxImg = 9;
+constexpr int kAccThreads = 128;
+constexpr int kChunk = 128;            // list entries staged per pass
+
+struct __align__(32) Rec {
+    double pa, pb, h;
+    float c[AST_MAX_PROPS];
+};
+static_assert(sizeof(Rec) == 32, "record is one 32-byte sector");
+
+struct P2 {
+    const double *pos, *h;
+    const double *prop[AST_MAX_PROPS];
+    double *out;
+    int64_t n;
+    int a_col, b_col, n_prop, kernel_id, shape;
+    Axis1 ax, ay;
+    int ntx, nty, n_img, img_shift;     // sort key = tile_key << img_shift | image
+    double shift_a[kMaxImg], shift_b[kMaxImg];
+    int64_t small_max_px, huge_min_tiles;
+    size_t map_stride;
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *smem /* >= 32 */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    uint32_t t = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0u;
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) smem[0] = t;
+    }
+    __syncthreads();
+    t = smem[0];
+    __syncthreads();
+    return t;
+}
+
+// exclusive prefix of v over the block (thread order), total in *total
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *smem /* >= 33 */, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem[lane] = winc - w;
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    uint32_t r = smem[warp] + inc - v;
+    *total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+// direct deposit of a small-footprint particle image: exact float64 mask, float32 shape, float64 atomics
+template <int SHAPE>
+__device__ __forceinline__ void deposit_small(const P2 &p, const Box2 &bb, double pa, double pb, double h, double R2,
+                                              const double *coef)
+{
+    const double inv_h2 = 1.0 / (h * h);
+    for (int xi = bb.x0; xi <= bb.x1; ++xi) {
+        const double dx2 = dist2(p.ax, pa, xi);
+        double *row = p.out + (size_t)xi * (size_t)p.ay.n;
+        for (int yi = bb.y0; yi <= bb.y1; ++yi) {
+            const double r2 = AST_DADD(dx2, dist2(p.ay, pb, yi));
+            if (r2 < R2) {
+                const float q = fast_sqrt((float)(r2 * inv_h2));
+                const double f = (double)shape_eval<SHAPE>(q);
+                for (int k = 0; k < p.n_prop; ++k) atomicAdd(row + k * p.map_stride + yi, coef[k] * f);
+            }
+        }
+    }
+}
+
+// K1.  DEPOSIT=false is the index-only variant used by ast_bin2d.
+template <int SHAPE, bool DEPOSIT>
+__global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
+                                                          uint64_t *__restrict__ block_huge)
+{
+    __shared__ uint32_t red[34];
+    const int64_t i = (int64_t)blockIdx.x * kBinThreads + threadIdx.x;
+    uint32_t npairs = 0, nhuge = 0;
+    if (i < p.n) {
+        const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i];
+        const double R2 = radius2(h);
+        bool need_rec = false;
+        double coef[AST_MAX_PROPS];
+        bool have_coef = false;
+        for (int m = 0; m < p.n_img; ++m) {
+            const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+            Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+            if (b.cls == CLS_SMALL) {
+                if (DEPOSIT) {
+                    if (!have_coef) {
+                        const double nrm = kernel_norm(p.kernel_id, h);
+                        for (int k = 0; k < p.n_prop; ++k) coef[k] = p.prop[k][i] * nrm;
+                        have_coef = true;
+                    }
+                    deposit_small<SHAPE>(p, b.bb, pa, pb, h, R2, coef);
+                }
+            } else if (b.cls == CLS_TILED) {
+                npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
+                need_rec = true;
+            } else if (b.cls == CLS_HUGE) {
+                ++nhuge;
+                need_rec = true;
+            }
+        }
+        if (need_rec && DEPOSIT) {
+            const double nrm = kernel_norm(p.kernel_id, h);
+            Rec r;
+            r.pa = pa0; r.pb = pb0; r.h = h;
+            for (int k = 0; k < AST_MAX_PROPS; ++k) r.c[k] = k < p.n_prop ? (float)(p.prop[k][i] * nrm) : 0.f;
+            rec[i] = r;
+        }
+    }
+    uint32_t tp = block_sum_u32(npairs, red);
+    uint32_t th = block_sum_u32(nhuge, red);
+    if (threadIdx.x == 0) {
+        block_pairs[blockIdx.x] = tp;
+        block_huge[blockIdx.x] = th;
+    }
+}
+
+// K3: pairs with global emit index in [w0, w1) are written to pairs[g - w0]; huge entries when write_huge.
+__global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t *__restrict__ pairs_excl,
+                                                           const uint64_t *__restrict__ huge_excl, uint64_t w0, uint64_t w1,
+                                                           uint64_t *__restrict__ pairs, uint64_t *__restrict__ huge,
+                                                           int write_huge, uint64_t huge_capacity)
+{
+    __shared__ uint32_t sm[34];
+    const uint64_t pbase = pairs_excl[blockIdx.x], pnext = pairs_excl[blockIdx.x + 1];
+    const uint64_t hbase = huge_excl[blockIdx.x], hnext = huge_excl[blockIdx.x + 1];
+    const bool any_pairs = pnext > pbase && pnext > w0 && pbase < w1;
+    const bool any_huge = write_huge && hnext > hbase;
+    if (!any_pairs && !any_huge) return;                    // uniform for the block
+    const int64_t i = (int64_t)blockIdx.x * kBinThreads + threadIdx.x;
+    double pa0 = 0, pb0 = 0, h = 0, R2 = 0;
+    uint32_t npairs = 0, nhuge = 0;
+    if (i < p.n) {
+        pa0 = p.pos[3 * i + p.a_col]; pb0 = p.pos[3 * i + p.b_col]; h = p.h[i];
+        R2 = radius2(h);
+        for (int m = 0; m < p.n_img; ++m) {
+            const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+            Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+            if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
+            else if (b.cls == CLS_HUGE) ++nhuge;
+        }
+    }
+    uint32_t tot;
+    uint64_t g = pbase + block_excl_scan_u32(npairs, sm, &tot);
+    uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
+    if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
+    for (int m = 0; m < p.n_img; ++m) {
+        const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+        Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+        if (b.cls == CLS_TILED) {
+            for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [&](uint32_t key) {
+                if (g >= w0 && g < w1)
+                    pairs[g - w0] = ((uint64_t)((key << p.img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
+                ++g;
+            });
+        } else if (b.cls == CLS_HUGE) {
+            if (write_huge && gh < huge_capacity) huge[gh] = ((uint64_t)m << 32) | (uint64_t)(uint32_t)i;
+            ++gh;
+        }
+    }
+}
+
+// K5: first / one-past-last sorted pair of every tile (arrays pre-zeroed)
+__global__ void tile_range_kernel(const uint64_t *__restrict__ sorted, int64_t n, int img_shift, uint32_t *__restrict__ tbeg,
+                                  uint32_t *__restrict__ tend)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = (uint32_t)(sorted[i] >> 32) >> img_shift;
+    if (i == 0 || ((uint32_t)(sorted[i - 1] >> 32) >> img_shift) != t) tbeg[t] = (uint32_t)i;
+    if (i == n - 1 || ((uint32_t)(sorted[i + 1] >> 32) >> img_shift) != t) tend[t] = (uint32_t)(i + 1);
+}
+
+// K6
+struct Acc {
+    const uint64_t *sorted;
+    const uint32_t *tbeg, *tend;
+    const uint64_t *huge;
+    uint32_t n_huge;
+    const Rec *rec;
+    double *out;
+    double x_min, y_min, dx, dy, inv_dx, inv_dy;
+    int nx, ny, ntx, nty, img_shift;
+    double shift_a[kMaxImg], shift_b[kMaxImg];
+    size_t map_stride;
+};
+
+template <int SHAPE, int NP>
+__global__ void __launch_bounds__(kAccThreads) tile_accum_kernel(Acc a)
+{
+    __shared__ float4 sP[kChunk];       // {ux*sx, uy*sy, sx, sy}  tile-relative, in units of h
+    __shared__ float4 sC[kChunk];       // {c0, c1, warp mask, -}
+    __shared__ int s_cnt[4];
+
+    const int tile = blockIdx.x;
+    const uint32_t beg = a.tbeg[tile], cnt = a.tend[tile] - beg;
+    const uint32_t total = cnt + a.n_huge;
+    if (total == 0) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tile / a.nty, ty = tile - tx * a.nty;
+    const int X0 = tx * TILE, Y0 = ty * TILE;
+    // this thread's pixels: 2 (x) by 4 (y) inside the warp's 16x16 sub-tile
+    const int xl = 16 * (warp >> 1) + 2 * (lane >> 2);
+    const int yl = 16 * (warp & 1) + 4 * (lane & 3);
+    const float xf0 = (float)xl, xf1 = (float)(xl + 1);
+    const float yf0 = (float)yl, yf1 = (float)(yl + 1), yf2 = (float)(yl + 2), yf3 = (float)(yl + 3);
+
+    float acc[NP][8];
+    double acc64[NP][8];
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
+
+    const double ox = (double)X0, oy = (double)Y0;
+
+    for (uint32_t base = 0; base < total; base += kChunk) {
+        // ---- stage up to kChunk list entries: float64 record -> tile-relative float32, per-warp cull mask
+        const uint32_t j = base + tid;
+        float4 P = make_float4(0.f, 0.f, 0.f, 0.f), C = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t mask = 0;
+        if (j < total) {
+            uint32_t idx, m;
+            if (j < cnt) {
+                const uint64_t e = a.sorted[beg + j];
+                idx = (uint32_t)e;
+                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
+            } else {
+                const uint64_t e = a.huge[j - cnt];
+                idx = (uint32_t)e;
+                m = (uint32_t)(e >> 32);
+            }
+            const Rec r = a.rec[idx];
+            const double ux = (r.pa + a.shift_a[m] - a.x_min) * a.inv_dx - ox;
+            const double uy = (r.pb + a.shift_b[m] - a.y_min) * a.inv_dy - oy;
+            const float sx = (float)(a.dx / r.h), sy = (float)(a.dy / r.h);
+            const float fx = (float)ux, fy = (float)uy;
+            P = make_float4(fx * sx, fy * sy, sx, sy);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float lox = 16.f * (float)(w >> 1), loy = 16.f * (float)(w & 1);
+                const float ddx = fmaxf(fmaxf(lox - fx, fx - (lox + 15.f)), 0.f) * sx;
+                const float ddy = fmaxf(fmaxf(loy - fy, fy - (loy + 15.f)), 0.f) * sy;
+                if (ddx * ddx + ddy * ddy < 4.0001f) mask |= 1u << w;
+            }
+            C = make_float4(r.c[0], NP > 1 ? r.c[1] : 0.f, __uint_as_float(mask), 0.f);
+        }
+        // compact the entries that touch at least one sub-tile
+        const unsigned ball = __ballot_sync(0xffffffffu, mask != 0);
+        __syncthreads();                                    // previous chunk fully consumed
+        if (lane == 0) s_cnt[warp] = __popc(ball);
+        __syncthreads();
+        int off = 0, nc = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int c = s_cnt[w];
+            off += w < warp ? c : 0;
+            nc += c;
+        }
+        if (mask != 0) {
+            const int dst = off + __popc(ball & ((1u << lane) - 1u));
+            sP[dst] = P;
+            sC[dst] = C;
+        }
+        __syncthreads();
+
+        // ---- accumulate: every warp walks the chunk, skipping entries that miss its sub-tile
+        for (int e = 0; e < nc; ++e) {
+            const float4 c = sC[e];
+            if (!((__float_as_uint(c.z) >> warp) & 1u)) continue;
+            const float4 q = sP[e];
+            float ax0 = fmaf(-xf0, q.z, q.x), ax1 = fmaf(-xf1, q.z, q.x);
+            ax0 *= ax0; ax1 *= ax1;
+            float by0 = fmaf(-yf0, q.w, q.y), by1 = fmaf(-yf1, q.w, q.y), by2 = fmaf(-yf2, q.w, q.y), by3 = fmaf(-yf3, q.w, q.y);
+            by0 *= by0; by1 *= by1; by2 *= by2; by3 *= by3;
+            const float axs[2] = { ax0, ax1 };
+            const float bys[4] = { by0, by1, by2, by3 };
+#pragma unroll
+            for (int jx = 0; jx < 2; ++jx)
+#pragma unroll
+                for (int jy = 0; jy < 4; ++jy) {
+                    const float f = shape_eval<SHAPE>(fast_sqrt(axs[jx] + bys[jy]));
+                    acc[0][jx * 4 + jy] = fmaf(c.x, f, acc[0][jx * 4 + jy]);
+                    if (NP > 1) acc[NP - 1][jx * 4 + jy] = fmaf(c.y, f, acc[NP - 1][jx * 4 + jy]);
+                }
+        }
+        // fold the chunk's float32 partial sums into the float64 accumulators
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) { acc64[k][jj] += (double)acc[k][jj]; acc[k][jj] = 0.f; }
+    }
+
+    // ---- one read-modify-write of the tile (each pixel belongs to exactly one thread of one CTA)
+#pragma unroll
+    for (int jx = 0; jx < 2; ++jx) {
+        const int xi = X0 + xl + jx;
+        if (xi >= a.nx) continue;
+#pragma unroll
+        for (int jy = 0; jy < 4; ++jy) {
+            const int yi = Y0 + yl + jy;
+            if (yi >= a.ny) continue;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
+                *o += acc64[k][jx * 4 + jy];
+            }
+        }
+    }
+}
+
+// exact contributor count (reference mask) per pixel, for parity tests
+__global__ void contrib_count_kernel(P2 p, int32_t *__restrict__ count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i];
+    const double R2 = radius2(h);
+    for (int m = 0; m < p.n_img; ++m) {
+        const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+        int x0, x1, y0, y1;
+        if (!range1(p.ax, pa, h, R2, x0, x1) || !range1(p.ay, pb, h, R2, y0, y1)) continue;
+        for (int xi = x0; xi <= x1; ++xi) {
+            const double dx2 = dist2(p.ax, pa, xi);
+            for (int yi = y0; yi <= y1; ++yi)
+                if (AST_DADD(dx2, dist2(p.ay, pb, yi)) < R2) atomicAdd(count + (size_t)xi * p.ay.n + yi, 1);
+        }
+    }
+}
+
+// bbox + class per particle image, for parity tests
+__global__ void bbox_cls_kernel(P2 p, int32_t *__restrict__ bbox, uint8_t *__restrict__ cls)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i];
+    const double R2 = radius2(h);
+    for (int m = 0; m < p.n_img; ++m) {
+        const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+        Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+        const int64_t j = (int64_t)m * p.n + i;
+        if (bbox) {
+            bbox[4 * j] = b.bb.x0; bbox[4 * j + 1] = b.bb.x1; bbox[4 * j + 2] = b.bb.y0; bbox[4 * j + 3] = b.bb.y1;
+        }
+        if (cls) cls[j] = (uint8_t)b.cls;
+    }
+}
+
+__global__ void kernel_eval_kernel(int kid, const double *__restrict__ r, const double *__restrict__ h, double *__restrict__ out,
+                                   int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = kernel_f64(kid, r[i], h[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+constexpr int64_t kDefaultSmallMaxPx = 16;
+constexpr int64_t kDefaultHugeMinTiles = 256;
+
+struct Layout2 {
+    int64_t nb;                 // bin blocks
+    int64_t ntiles;
+    int64_t pair_cap, huge_cap;
+    uint64_t *block_pairs, *block_huge;   // nb + 1 each
+    Rec *rec;
+    uint64_t *pairs_a, *pairs_b, *huge;
+    uint32_t *tbeg, *tend;
+    void *sort_ws;
+    size_t bytes;
+};
+
+static int validate2(const ast_project2d_params *p)
+{
+    AST_REQUIRE(p != nullptr, "params is null");
+    AST_REQUIRE(p->n >= 0 && p->n < (int64_t)0xffffffffll, "n = %lld out of range [0, 2^32-1)", (long long)p->n);
+    AST_REQUIRE(p->axis >= 0 && p->axis <= 2, "axis = %d is not 0, 1 or 2", p->axis);
+    AST_REQUIRE(p->nx > 0 && p->ny > 0, "image_size (%d, %d) must be positive", p->nx, p->ny);
+    AST_REQUIRE((int64_t)((p->nx + TILE - 1) / TILE) * ((p->ny + TILE - 1) / TILE) < (1ll << 27), "image too large");
+    AST_REQUIRE(kernel_valid(p->kernel_id), "unknown kernel id %d", p->kernel_id);
+    AST_REQUIRE(p->n_prop >= 1 && p->n_prop <= AST_MAX_PROPS, "n_prop = %d not in [1, %d]", p->n_prop, AST_MAX_PROPS);
+    AST_REQUIRE(p->x_max > p->x_min && p->y_max > p->y_min, "empty or inverted map bounds");
+    if (p->flags & AST_FLAG_PERIODIC) AST_REQUIRE(p->box_a > 0 && p->box_b > 0, "periodic projection needs box_a, box_b > 0");
+    AST_REQUIRE(p->pair_capacity >= 0 && p->pair_capacity < (1ll << 32), "pair_capacity out of range");
+    AST_REQUIRE(p->huge_capacity >= 0 && p->huge_capacity < (1ll << 32), "huge_capacity out of range");
+    return AST_OK;
+}
+
+static Layout2 layout2(const ast_project2d_params *p, void *ws)
+{
+    Layout2 L;
+    L.nb = (p->n + kBinThreads - 1) / kBinThreads;
+    if (L.nb < 1) L.nb = 1;
+    L.ntiles = (int64_t)((p->nx + TILE - 1) / TILE) * ((p->ny + TILE - 1) / TILE);
+    L.pair_cap = p->pair_capacity > 0 ? p->pair_capacity : 1;
+    L.huge_cap = p->huge_capacity > 0 ? p->huge_capacity : 1;
+    Carver c(ws);
+    L.block_pairs = c.take<uint64_t>(L.nb + 1);
+    L.block_huge = c.take<uint64_t>(L.nb + 1);
+    L.rec = c.take<Rec>(p->n > 0 ? p->n : 1);
+    L.pairs_a = c.take<uint64_t>(L.pair_cap);
+    L.pairs_b = c.take<uint64_t>(L.pair_cap);
+    L.huge = c.take<uint64_t>(L.huge_cap);
+    L.tbeg = c.take<uint32_t>(L.ntiles);
+    L.tend = c.take<uint32_t>(L.ntiles);
+    L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
+    L.bytes = c.bytes();
+    return L;
+}
+
+static P2 make_p2(const ast_project2d_params *p, const double *pos, const double *h, const double *const *prop, double *out)
+{
+    P2 a;
+    a.pos = pos; a.h = h; a.out = out;
+    for (int k = 0; k < AST_MAX_PROPS; ++k) a.prop[k] = (prop && k < p->n_prop) ? prop[k] : nullptr;
+    a.n = p->n;
+    plane_columns(p->axis, a.a_col, a.b_col);
+    a.n_prop = p->n_prop;
+    a.kernel_id = p->kernel_id;
+    a.shape = kernel_shape(p->kernel_id);
+    a.ax = make_axis(p->x_min, p->x_max, p->nx);
+    a.ay = make_axis(p->y_min, p->y_max, p->ny);
+    a.ntx = (p->nx + TILE - 1) / TILE;
+    a.nty = (p->ny + TILE - 1) / TILE;
+    const bool per = (p->flags & AST_FLAG_PERIODIC) != 0;
+    a.n_img = per ? 9 : 1;
+    a.img_shift = per ? 4 : 0;
+    for (int m = 0; m < kMaxImg; ++m) {
+        a.shift_a[m] = per ? (double)(m / 3 - 1) * p->box_a : 0.0;   // image m = 3*(ia+1) + (ib+1)
+        a.shift_b[m] = per ? (double)(m % 3 - 1) * p->box_b : 0.0;
+    }
+    a.small_max_px = p->small_max_px >= 0 ? p->small_max_px : kDefaultSmallMaxPx;
+    a.huge_min_tiles = p->huge_min_tiles >= 0 ? p->huge_min_tiles : kDefaultHugeMinTiles;
+    a.map_stride = (size_t)p->nx * (size_t)p->ny;
+    return a;
+}
+
+template <int SHAPE>
+static void launch_accum(int np, const Acc &a, int64_t ntiles, cudaStream_t s)
+{
+    if (np == 1) tile_accum_kernel<SHAPE, 1><<<(unsigned)ntiles, kAccThreads, 0, s>>>(a);
+    else tile_accum_kernel<SHAPE, 2><<<(unsigned)ntiles, kAccThreads, 0, s>>>(a);
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+extern "C" int ast_project2d_workspace_bytes(const ast_project2d_params *p, size_t *bytes)
+{
+    int rc = validate2(p);
+    if (rc) return rc;
+    AST_REQUIRE(bytes != nullptr, "bytes is null");
+    *bytes = layout2(p, nullptr).bytes;
+    return AST_OK;
+}
+
+extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, const double *h, const double *const *prop,
+                             double *out, void *workspace, size_t workspace_bytes, void *stream, ast_project2d_stats *stats)
+{
+    int rc = validate2(p);
+    if (rc) return rc;
+    AST_REQUIRE(out != nullptr, "out is null");
+    AST_REQUIRE(p->n == 0 || (pos && h && prop), "null input pointer");
+    for (int k = 0; k < p->n_prop && p->n > 0; ++k) AST_REQUIRE(prop[k] != nullptr, "prop[%d] is null", k);
+    Layout2 L = layout2(p, workspace);
+    if (workspace == nullptr || workspace_bytes < L.bytes) {
+        set_error("workspace too small: need %zu bytes, have %zu", L.bytes, workspace_bytes);
+        return AST_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    StageTimer tm((p->flags & AST_FLAG_TIMING) != 0, s);
+    ast_project2d_stats st;
+    memset(&st, 0, sizeof st);
+    P2 a = make_p2(p, pos, h, prop, out);
+
+    tm.begin(7);
+    StageTimer tk((p->flags & AST_FLAG_TIMING) != 0, s);
+    tk.begin(6);
+    if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * a.map_stride * p->n_prop, s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    tk.end();
+    uint64_t totals[2] = { 0, 0 };
+    if (p->n > 0) {
+        tk.begin(0);
+        if (a.shape == SHAPE_CUBIC) bin_kernel<SHAPE_CUBIC, true><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        else bin_kernel<SHAPE_WENDLAND, true><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        tk.end();
+        tk.begin(1);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
+        tk.end();
+        st.n_launches += 3;
+        AST_CUDA_TRY(cudaGetLastError());
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    st.n_pairs = (int64_t)totals[0];
+    st.n_huge = (int64_t)totals[1];
+    if (totals[1] > (uint64_t)L.huge_cap) {
+        set_error("huge_capacity too small: need %llu entries, have %lld", (unsigned long long)totals[1], (long long)L.huge_cap);
+        if (stats) *stats = st;
+        return AST_EWORKSPACE;
+    }
+    if (totals[0] > 0 && p->pair_capacity <= 0) {
+        set_error("pair_capacity is 0 but %llu pairs are needed", (unsigned long long)totals[0]);
+        if (stats) *stats = st;
+        return AST_EWORKSPACE;
+    }
+    if (totals[0] + totals[1] > 0) {
+        const uint64_t cap = (uint64_t)L.pair_cap;
+        const int64_t rounds = totals[0] ? (int64_t)((totals[0] + cap - 1) / cap) : 1;
+        const int key_bits = ceil_log2_u64((uint64_t)L.ntiles) + a.img_shift;
+        Acc c;
+        c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
+        c.x_min = a.ax.vmin; c.y_min = a.ay.vmin; c.dx = a.ax.d; c.dy = a.ay.d; c.inv_dx = a.ax.inv_d; c.inv_dy = a.ay.inv_d;
+        c.nx = p->nx; c.ny = p->ny; c.ntx = a.ntx; c.nty = a.nty; c.img_shift = a.img_shift;
+        for (int m = 0; m < kMaxImg; ++m) { c.shift_a[m] = a.shift_a[m]; c.shift_b[m] = a.shift_b[m]; }
+        c.map_stride = a.map_stride;
+        for (int64_t r = 0; r < rounds; ++r) {
+            const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
+            const int64_t nw = (int64_t)(w1 - w0);
+            tk.begin(2);
+            emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.block_pairs, L.block_huge, w0, w1, L.pairs_a, L.huge, r == 0,
+                                                              (uint64_t)L.huge_cap);
+            tk.end();
+            st.n_launches += 1;
+            int in_b = 0, nl = 0;
+            tk.begin(3);
+            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32, key_bits, L.sort_ws, s, &in_b, &nl));
+            tk.end();
+            st.n_launches += nl;
+            tk.begin(4);
+            AST_CUDA_TRY(cudaMemsetAsync(L.tbeg, 0, sizeof(uint32_t) * L.ntiles, s));
+            AST_CUDA_TRY(cudaMemsetAsync(L.tend, 0, sizeof(uint32_t) * L.ntiles, s));
+            c.sorted = in_b ? L.pairs_b : L.pairs_a;
+            if (nw > 0) {
+                tile_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
+                st.n_launches += 1;
+            }
+            tk.end();
+            c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
+            tk.begin(5);
+            if (a.shape == SHAPE_CUBIC) launch_accum<SHAPE_CUBIC>(p->n_prop, c, L.ntiles, s);
+            else launch_accum<SHAPE_WENDLAND>(p->n_prop, c, L.ntiles, s);
+            tk.end();
+            st.n_launches += 1;
+            AST_CUDA_TRY(cudaGetLastError());
+        }
+        st.n_rounds = rounds;
+    }
+    tm.end();
+    if (p->flags & AST_FLAG_TIMING) {
+        float total_ms[8];
+        tk.collect(st.stage_ms, 8);
+        tm.collect(total_ms, 8);
+        st.stage_ms[7] = total_ms[7];
+    }
+    if (stats) *stats = st;
+    return AST_OK;
+}
+
+extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const double *h, int32_t *bbox, uint8_t *cls,
+                         uint64_t *pairs_emit, uint64_t *pairs_sorted, uint64_t *huge, int64_t *counts, void *workspace,
+                         size_t workspace_bytes, void *stream)
+{
+    int rc = validate2(p);
+    if (rc) return rc;
+    AST_REQUIRE(p->n == 0 || (pos && h), "null input pointer");
+    Layout2 L = layout2(p, workspace);
+    if (workspace == nullptr || workspace_bytes < L.bytes) {
+        set_error("workspace too small: need %zu bytes, have %zu", L.bytes, workspace_bytes);
+        return AST_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    P2 a = make_p2(p, pos, h, nullptr, nullptr);
+    uint64_t totals[2] = { 0, 0 };
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    if (p->n > 0) {
+        if (bbox || cls) bbox_cls_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, bbox, cls);
+        bin_kernel<SHAPE_CUBIC, false><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
+        AST_CUDA_TRY(cudaGetLastError());
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (counts) { counts[0] = (int64_t)totals[0]; counts[1] = (int64_t)totals[1]; }
+    if (totals[0] > (uint64_t)p->pair_capacity || totals[1] > (uint64_t)p->huge_capacity) {
+        set_error("capacity too small: need %llu pairs and %llu huge entries", (unsigned long long)totals[0],
+                  (unsigned long long)totals[1]);
+        return AST_EWORKSPACE;
+    }
+    if (totals[0] + totals[1] > 0) {
+        emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, totals[0], L.pairs_a, L.huge, 1,
+                                                          (uint64_t)L.huge_cap);
+        AST_CUDA_TRY(cudaGetLastError());
+        if (pairs_emit && totals[0])
+            AST_CUDA_TRY(cudaMemcpyAsync(pairs_emit, L.pairs_a, sizeof(uint64_t) * totals[0], cudaMemcpyDeviceToDevice, s));
+        if (huge && totals[1]) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * totals[1], cudaMemcpyDeviceToDevice, s));
+        if (pairs_sorted && totals[0]) {
+            int in_b = 0;
+            const int key_bits = ceil_log2_u64((uint64_t)L.ntiles) + a.img_shift;
+            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, (int64_t)totals[0], 32, key_bits, L.sort_ws, s, &in_b));
+            AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? L.pairs_b : L.pairs_a, sizeof(uint64_t) * totals[0],
+                                         cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    AST_CUDA_TRY(cudaStreamSynchronize(s));
+    return AST_OK;
+}
+
+extern "C" int ast_contrib_count2d(const ast_project2d_params *p, const double *pos, const double *h, int32_t *count, void *stream)
+{
+    int rc = validate2(p);
+    if (rc) return rc;
+    AST_REQUIRE(count != nullptr && (p->n == 0 || (pos && h)), "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    P2 a = make_p2(p, pos, h, nullptr, nullptr);
+    AST_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t) * a.map_stride, s));
+    if (p->n > 0) contrib_count_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, s>>>(a, count);
+    AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
+}
+
+extern "C" int ast_kernel_eval(int kernel_id, const double *r, const double *h, double *out, int64_t n, void *stream)
+{
+    AST_REQUIRE(kernel_valid(kernel_id), "unknown kernel id %d", kernel_id);
+    AST_REQUIRE(n >= 0 && (n == 0 || (r && h && out)), "null pointer or negative n");
+    if (n > 0) kernel_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kernel_id, r, h, out, n);
+    AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
+}
+
+extern "C" int ast_sort_workspace_bytes(int64_t n, size_t *bytes)
+{
+    AST_REQUIRE(bytes != nullptr && n >= 0, "bad argument");
+    *bytes = sort_workspace_bytes(n);
+    return AST_OK;
+}
+
+extern "C" int ast_radix_sort_u64(uint64_t *keys, uint64_t *tmp, int64_t n, int bit_lo, int n_bits, void *workspace,
+                                  size_t workspace_bytes, void *stream, int *result_in_tmp)
+{
+    AST_REQUIRE(n >= 0 && n < (1ll << 32), "n out of range");
+    AST_REQUIRE(bit_lo >= 0 && n_bits >= 0 && bit_lo + n_bits <= 64, "bad bit range");
+    AST_REQUIRE(result_in_tmp != nullptr, "result_in_tmp is null");
+    if (workspace_bytes < sort_workspace_bytes(n) || (n > 0 && (!keys || !tmp || !workspace))) {
+        set_error("sort workspace too small or null buffers");
+        return AST_EWORKSPACE;
+    }
+    AST_CUDA_TRY(radix_sort_u64(keys, tmp, n, bit_lo, n_bits, workspace, (cudaStream_t)stream, result_in_tmp));
+    return AST_OK;
+}

@@ -1,0 +1,2 @@
+"""Analysis tools on the hot path (the reference's tools/__init__.py:5-7 also exports periodic-box and
+array-reorder helpers; those are out of scope here)."""

@@ -1,0 +1,129 @@
+"""Device-side driver of the 2-D projection: owns the torch buffers (inputs, maps, workspace) and calls the
+C ABI (include/astro_sph_b200.h: ast_project2d).  PyTorch is used for device memory and streams only.
+
+``Projector2D`` keeps its workspace between calls, so repeated projections of same-sized inputs (bench loops,
+many maps of one snapshot) do not reallocate.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ... import _lib
+from ..._CoordinateAxes import CoordinateAxes
+
+
+def _axis_index(projection_axis):
+    if isinstance(projection_axis, CoordinateAxes):
+        return projection_axis.value
+    if hasattr(projection_axis, "value") and projection_axis.value in (0, 1, 2):      # the reference's own enum
+        return int(projection_axis.value)
+    if isinstance(projection_axis, str):
+        return CoordinateAxes.from_string(projection_axis).value
+    if isinstance(projection_axis, (int, np.integer)) and 0 <= int(projection_axis) <= 2:
+        return int(projection_axis)
+    raise ValueError(f"projection_axis must be a CoordinateAxes member, got {projection_axis!r}")
+
+
+class Projector2D:
+    """Reusable projection context on one CUDA device."""
+
+    def __init__(self, device=None, pair_capacity=None, huge_capacity=1 << 20, small_max_px=-1, huge_min_tiles=-1):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        torch = self.torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.pair_capacity = pair_capacity
+        self.huge_capacity = int(huge_capacity)
+        self.small_max_px = int(small_max_px)
+        self.huge_min_tiles = int(huge_min_tiles)
+        self._ws = None
+        self.last_stats = None
+
+    # ---- parameters -------------------------------------------------------------------------------------
+    def _params(self, n, image_size, axis, bounds, kernel, n_prop, periodic, box, timing, accumulate):
+        p = _lib.Project2DParams()
+        p.n = int(n)
+        p.axis = _axis_index(axis)
+        p.nx, p.ny = int(image_size[0]), int(image_size[1])
+        p.kernel_id = _lib.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
+        p.n_prop = int(n_prop)
+        p.flags = (_lib.FLAG_PERIODIC if periodic else 0) | (_lib.FLAG_TIMING if timing else 0) | \
+                  (_lib.FLAG_ACCUMULATE if accumulate else 0)
+        p.x_min, p.x_max, p.y_min, p.y_max = (float(v) for v in bounds)
+        if periodic:
+            if box is None:
+                raise ValueError("periodic=True needs box_size")
+            if np.isscalar(box):
+                ba = bb = float(box)
+            else:
+                box = tuple(float(v) for v in box)
+                cols = CoordinateAxes(p.axis).plane_columns
+                ba, bb = (box[cols[0]], box[cols[1]]) if len(box) == 3 else box
+            p.box_a, p.box_b = ba, bb
+        p.small_max_px = self.small_max_px
+        p.huge_min_tiles = self.huge_min_tiles
+        cap = self.pair_capacity
+        if cap is None:
+            cap = min(max(8 * int(n), 1 << 20), 1 << 30)
+        p.pair_capacity = int(cap)
+        p.huge_capacity = int(self.huge_capacity)
+        return p
+
+    def _workspace(self, p):
+        need = C.c_size_t(0)
+        _lib.check(self.lib.ast_project2d_workspace_bytes(C.byref(p), C.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != self.device:
+            self._ws = None
+            self._ws = self.torch.empty(need.value, dtype=self.torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- device-resident call -----------------------------------------------------------------------------
+    def project(self, pos, h, props, image_size, axis, bounds, kernel="cubic_spline_3d", periodic=False, box=None,
+                out=None, timing=False, accumulate=False, stream=None):
+        """pos (N,3), h (N,), props = tensor (N,) or list of <= 2 tensors: float64 CUDA tensors.
+        Returns the float64 CUDA map(s): (nx,ny) for a single tensor, (P,nx,ny) for a list."""
+        torch = self.torch
+        single = not isinstance(props, (list, tuple))
+        plist = [props] if single else list(props)
+        if not 1 <= len(plist) <= _lib.MAX_PROPS:
+            raise ValueError(f"between 1 and {_lib.MAX_PROPS} weight arrays per pass, got {len(plist)}")
+        n = pos.shape[0]
+        for t, shape in [(pos, (n, 3)), (h, (n,))] + [(q, (n,)) for q in plist]:
+            if t.dtype != torch.float64 or tuple(t.shape) != shape or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("device inputs must be contiguous float64 CUDA tensors of shapes (N,3), (N,), (N,)")
+        p = self._params(n, image_size, axis, bounds, kernel, len(plist), periodic, box, timing, accumulate)
+        if out is None:
+            out = torch.empty((len(plist), p.nx, p.ny), dtype=torch.float64, device=self.device)
+        elif out.dtype != torch.float64 or out.numel() != len(plist) * p.nx * p.ny or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float64 tensor of n_prop*nx*ny elements")
+        prop_ptrs = (C.c_void_p * _lib.MAX_PROPS)(*[q.data_ptr() for q in plist] + [None] * (_lib.MAX_PROPS - len(plist)))
+        stats = _lib.Project2DStats()
+        with torch.cuda.device(self.device):
+            while True:
+                ws = self._workspace(p)
+                rc = self.lib.ast_project2d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), prop_ptrs, _lib.ptr(out), _lib.ptr(ws),
+                                            C.c_size_t(ws.numel()), _lib.stream_ptr(stream), C.byref(stats))
+                if rc == _lib.AST_EWORKSPACE and stats.n_huge > p.huge_capacity:
+                    self.huge_capacity = int(stats.n_huge * 1.25) + 1024     # grow the large-h list and retry
+                    p.huge_capacity = self.huge_capacity
+                    continue
+                _lib.check(rc)
+                break
+        self.last_stats = dict(n_pairs=stats.n_pairs, n_huge=stats.n_huge, n_rounds=stats.n_rounds,
+                               n_launches=stats.n_launches, stage_ms=list(stats.stage_ms))
+        out = out.view(len(plist), p.nx, p.ny)
+        return out[0] if single else out
+
+    # ---- host call (numpy in, numpy out): what create_image uses -------------------------------------------
+    def project_host(self, positions, smoothing_lengths, props, image_size, axis, bounds, kernel="cubic_spline_3d",
+                     periodic=False, box=None, stream=None):
+        torch = self.torch
+        single = not isinstance(props, (list, tuple))
+        plist = [props] if single else list(props)
+        dev = self.device
+        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+        pos_d, h_d = to_dev(positions), to_dev(smoothing_lengths)
+        props_d = [to_dev(q) for q in plist]
+        out = self.project(pos_d, h_d, props_d[0] if single else props_d, image_size, axis, bounds, kernel, periodic, box,
+                           stream=stream)
+        return out.cpu().numpy()

@@ -1,0 +1,174 @@
+/*
+ * astro_sph_b200.h -- C ABI of the B200-native SPH deposition / smoothing-length library
+ * (libastsph_b200.so, built from astro-sph-tools_b200/csrc by nvcc for sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of QuasarX1/astro-sph-tools.  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference/src/astro_sph_tools/).  In the
+ * reference the FFI boundary is Python -> Cython, crossed once PER PIXEL
+ * (tools/projections/_pixel_calculations.pyx:9-10 calculate_pixel_value, called from
+ * tools/projections/_projector.py:53-71); here it is crossed once PER MAP.
+ *
+ * Conventions
+ *   - every function returns an ast_status (0 = ok); ast_last_error() gives the message of the last
+ *     failure on the calling thread;
+ *   - all data pointers are DEVICE pointers unless the parameter is documented "host";
+ *   - the library never allocates or frees device memory: inputs, outputs and workspace are caller-owned
+ *     (the Python host layer hands torch-owned buffers in by raw pointer);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it except where a function
+ *     is documented to synchronise;
+ *   - positions are (N,3) row-major float64 exactly as the reference readers hand them out
+ *     (io/data_structures/_SnapshotBase.py:708-725), h and the per-particle weights are (N,) float64
+ *     (:599-616, :618-637); maps are float64 row-major out[xi*ny + yi] like the reference's img[xi, yi]
+ *     (tools/projections/_projector.py:88,117).
+ */
+#ifndef ASTRO_SPH_B200_H
+#define ASTRO_SPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AST_ABI_VERSION 1
+#define AST_MAX_PROPS 2          /* weight fields deposited in one pass (mass and mass*T for config 2) */
+#define AST_TILE 32              /* screen tile edge in pixels (tile key = tx * ceil(ny/32) + ty) */
+#define AST_BRICK 8              /* voxel brick edge for the 3-D grid (brick key = (bx*nby + by)*nbz + bz) */
+
+typedef enum ast_status {
+    AST_OK = 0,
+    AST_EINVAL = 1,              /* bad argument (shape, axis, kernel id, null pointer) */
+    AST_EWORKSPACE = 2,          /* workspace or a capacity is too small; see ast_last_error() */
+    AST_ECUDA = 3,               /* a CUDA runtime call or kernel launch failed */
+    AST_EUNSUPPORTED = 4
+} ast_status;
+
+/* SPH kernels W(r,h); all have support r < 2h, the reference's hard mask (_pixel_calculations.pyx:31). */
+typedef enum ast_kernel {
+    AST_KERNEL_CUBIC_SPLINE_3D = 0,   /* the reference's `quartic_spline_kernel` (tools/projections/_kernels.pyx:9-20):
+                                         M4 cubic spline, 1/(pi h^3) normalisation */
+    AST_KERNEL_WENDLAND_C2_2D = 1,    /* 7/(pi H^2) (1-u)^4 (1+4u), u = r/H, H = 2h  (surface density) */
+    AST_KERNEL_WENDLAND_C2_3D = 2,    /* 21/(2 pi H^3) (1-u)^4 (1+4u) */
+    AST_KERNEL_CUBIC_SPLINE_2D = 3    /* M4 cubic spline with 10/(7 pi h^2) */
+} ast_kernel;
+
+enum {
+    AST_FLAG_PERIODIC = 1,       /* deposit the 9 (2-D) / 27 (3-D) periodic images, shifts ia*box_a etc. */
+    AST_FLAG_ACCUMULATE = 2,     /* add to `out` instead of zeroing it first */
+    AST_FLAG_TIMING = 4          /* record CUDA events around every stage and return stage_ms (synchronises) */
+};
+
+/* ---- 2-D line-of-sight projection ------------------------------------------------------------------
+ * Replaces create_image / process_chunk / calculate_pixel_value
+ * (tools/projections/_projector.py:75-120, :13-73, _pixel_calculations.pyx:9-36):
+ *   out[p][xi][yi] = sum_i prop_p[i] * W(sqrt(r2), h_i)  over  r2 = (pa - X)^2 + (pb - Y)^2 < (2 h_i)^2
+ *   X = x_min + xi*(x_max-x_min)/nx, Y = y_min + yi*(y_max-y_min)/ny   (pixel LOWER corner)
+ *   (pa, pb) = position columns (1,2) / (0,2) / (0,1) for axis 0 / 1 / 2. */
+typedef struct ast_project2d_params {
+    int64_t n;                   /* particles */
+    int32_t axis;                /* 0 = X, 1 = Y, 2 = Z  (CoordinateAxes, _CoordinateAxes.py:7-9) */
+    int32_t nx, ny;              /* image_size */
+    int32_t kernel_id;           /* ast_kernel */
+    int32_t n_prop;              /* 1..AST_MAX_PROPS weight arrays -> that many maps */
+    int32_t flags;
+    double x_min, x_max, y_min, y_max;
+    double box_a, box_b;         /* periodic lengths along the two in-plane axes (AST_FLAG_PERIODIC) */
+    int64_t small_max_px;        /* bbox area (pixels) up to which a particle is deposited directly; <0 = default */
+    int64_t huge_min_tiles;      /* tile-bbox count above which a particle goes to the global list; <0 = default */
+    int64_t pair_capacity;       /* (tile, particle) pairs the workspace holds per round */
+    int64_t huge_capacity;       /* entries of the global large-h list */
+} ast_project2d_params;
+
+typedef struct ast_project2d_stats {
+    int64_t n_pairs;             /* (tile, particle-image) pairs emitted */
+    int64_t n_huge;              /* particle-images in the global large-h list */
+    int64_t n_rounds;            /* passes over the pair window (1 unless pair_capacity < n_pairs) */
+    int64_t n_launches;          /* kernels launched by this call */
+    float stage_ms[8];           /* AST_FLAG_TIMING: 0 bin+direct deposit, 1 scan, 2 emit, 3 sort, 4 tile ranges,
+                                    5 tile accumulate, 6 memset, 7 total */
+} ast_project2d_stats;
+
+int ast_project2d_workspace_bytes(const ast_project2d_params *p, size_t *bytes /* host */);
+
+/* prop: HOST array of n_prop DEVICE pointers.  out: n_prop*nx*ny doubles.  Synchronises the stream once
+ * (to read the pair count) unless every particle is deposited directly.  stats: host, nullable. */
+int ast_project2d(const ast_project2d_params *p, const double *pos, const double *h,
+                  const double *const *prop, double *out, void *workspace, size_t workspace_bytes,
+                  void *stream, ast_project2d_stats *stats);
+
+/* ---- index work, exposed for the bit-exact parity tests (no reference symbol: the reference is a gather;
+ * the definitions follow _pixel_calculations.pyx:11-14,30-31, see DESIGN.md "Index work") ------------
+ * bbox: n_img*N*4 int32 (x0,x1,y0,y1 inclusive; empty = 0,-1,0,-1), row j = m*N + i.
+ * cls:  n_img*N uint8 (0 empty, 1 direct, 2 tiled, 3 global list).
+ * pairs_emit / pairs_sorted: pair_capacity uint64 each, element = (sort_key << 32) | particle,
+ *   sort_key = tile_key * (periodic ? 16 : 1) + image.  huge: huge_capacity uint64 = (image << 32) | particle.
+ * counts (host): [0] pairs, [1] huge.  Any output pointer may be null.  Synchronises. */
+int ast_bin2d(const ast_project2d_params *p, const double *pos, const double *h,
+              int32_t *bbox, uint8_t *cls, uint64_t *pairs_emit, uint64_t *pairs_sorted, uint64_t *huge,
+              int64_t *counts, void *workspace, size_t workspace_bytes, void *stream);
+
+/* exact contributor count per pixel: the reference mask r2 < (2h)^2 in float64 (int32 map nx*ny) */
+int ast_contrib_count2d(const ast_project2d_params *p, const double *pos, const double *h, int32_t *count,
+                        void *stream);
+
+/* ---- SPH kernel evaluation, replaces quartic_spline_kernel(double[:] r, double[:] h)
+ * (tools/projections/_kernels.pyx:9-20) for any ast_kernel, float64 ------------------------------- */
+int ast_kernel_eval(int kernel_id, const double *r, const double *h, double *out, int64_t n, void *stream);
+
+/* ---- device radix sort of 64-bit elements by bits [bit_lo, bit_lo+n_bits), stable.  keys and tmp hold n
+ * elements; *result_in_tmp (host) tells which buffer has the result.  Exposed for tests. */
+int ast_sort_workspace_bytes(int64_t n, size_t *bytes);
+int ast_radix_sort_u64(uint64_t *keys, uint64_t *tmp, int64_t n, int bit_lo, int n_bits, void *workspace,
+                       size_t workspace_bytes, void *stream, int *result_in_tmp);
+
+/* ---- 3-D voxel gridding (EXTENSION named by BASELINE.json; no reference function; same rules as 2-D:
+ * voxel lower-corner sample, r2 = (dx^2+dy^2)+dz^2 < (2h)^2) -------------------------------------- */
+typedef struct ast_grid3d_params {
+    int64_t n;
+    int32_t nx, ny, nz;
+    int32_t kernel_id;
+    int32_t flags;
+    int32_t reserved;
+    double lo[3], hi[3];
+    double box[3];
+    int64_t small_max_vox;       /* bbox volume up to which a particle is deposited directly; <0 = default */
+    int64_t huge_min_bricks;     /* brick-bbox count above which a particle goes to the global list; <0 = default */
+    int64_t pair_capacity;
+    int64_t huge_capacity;
+} ast_grid3d_params;
+
+int ast_grid3d_workspace_bytes(const ast_grid3d_params *p, size_t *bytes);
+int ast_grid3d(const ast_grid3d_params *p, const double *pos, const double *h, const double *prop,
+               double *out, void *workspace, size_t workspace_bytes, void *stream, ast_project2d_stats *stats);
+
+/* ---- smoothing lengths by k nearest neighbours, replaces the KDTree branch of
+ * SnapshotSWIFT.get_smoothing_lengths (io/SWIFT/_SnapshotSWIFT.py:62-83):
+ *   h_out[i] = K-th smallest sqrt((dx*dx+dy*dy)+dz*dz) over all particles j, i itself included;
+ *   box > 0: each delta is first wrapped by -+box when |delta| > box/2 (scipy boxsize semantics) and
+ *   positions must satisfy 0 <= x < box.  idx_out (nullable): N*k int32 neighbour indices, ascending
+ *   (distance, index).  dist_out (nullable): N*k float64.  Positions must lie in [lo, hi] per axis (open
+ *   box) -- the cell grid is built over that extent. */
+typedef struct ast_knn_params {
+    int64_t n;
+    int32_t k;
+    int32_t flags;
+    double box;                  /* > 0: periodic cube [0, box)^3 ; <= 0: open */
+    double lo[3], hi[3];         /* extent of the positions (open box); ignored when periodic */
+    double cell_target;          /* mean particles per cell; <= 0 = default */
+} ast_knn_params;
+
+int ast_knn_workspace_bytes(const ast_knn_params *p, size_t *bytes);
+int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_out, int32_t *idx_out, double *dist_out,
+              void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- misc ---- */
+const char *ast_last_error(void);
+int ast_abi_version(void);
+int ast_tile_size(void);
+int ast_device_sm_count(int *sm_count /* host */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASTRO_SPH_B200_H */

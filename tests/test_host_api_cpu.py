@@ -1,0 +1,90 @@
+"""CPU-only checks of the host layer: the C-ABI library loads and exports every declared symbol, argument
+validation mirrors the reference's Cython errors, and the product path fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from astro_sph_tools_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "astro_sph_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*(ast_[a-z0-9_]+)\s*\(", hdr, re.M))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ast_abi_version() == 1 and lib.ast_tile_size() == 32
+
+
+def test_struct_layout_matches_header():
+    from astro_sph_tools_b200 import _lib
+    assert C.sizeof(_lib.Project2DParams) == 8 + 6 * 4 + 6 * 8 + 4 * 8
+    assert C.sizeof(_lib.Project2DStats) == 4 * 8 + 8 * 4
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """validation happens before any CUDA call, so it can be exercised on a CPU box"""
+    from astro_sph_tools_b200 import _lib
+    lib = _lib.load()
+    p = _lib.Project2DParams()
+    need = C.c_size_t(0)
+    p.n = 10; p.axis = 5; p.nx = p.ny = 8; p.n_prop = 1; p.x_max = p.y_max = 1.0
+    assert lib.ast_project2d_workspace_bytes(C.byref(p), C.byref(need)) == _lib.AST_EINVAL
+    assert b"axis" in lib.ast_last_error()
+    p.axis = 2; p.kernel_id = 17
+    assert lib.ast_project2d_workspace_bytes(C.byref(p), C.byref(need)) == _lib.AST_EINVAL
+    p.kernel_id = 0; p.pair_capacity = 1000; p.huge_capacity = 10
+    assert lib.ast_project2d_workspace_bytes(C.byref(p), C.byref(need)) == _lib.AST_OK and need.value > 1000 * 16
+    with pytest.raises(ValueError):
+        _lib.check(_lib.AST_EINVAL)
+
+
+def test_create_image_validation_mirrors_reference_errors():
+    from astro_sph_tools_b200 import CoordinateAxes
+    from astro_sph_tools_b200.tools.projections import create_image
+    pos = np.zeros((4, 3)); h = np.ones(4); a = np.ones(4)
+    args = ((8, 8), 4, CoordinateAxes.Z, 0.0, 1.0, 0.0, 1.0)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch, expected 'double' but got 'float'"):
+        create_image(pos.astype(np.float32), h, a, *args)
+    with pytest.raises(ValueError, match="wrong number of dimensions"):
+        create_image(pos[:, 0], h, a, *args)
+    with pytest.raises(NotImplementedError):
+        create_image(pos, h, a, *args, kernel_func=lambda r, hh: r)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from astro_sph_tools_b200 import CoordinateAxes
+    from astro_sph_tools_b200.tools.projections import create_image, quartic_spline_kernel
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        create_image(np.zeros((4, 3)), np.ones(4), np.ones(4), (8, 8), 4, CoordinateAxes.Z, 0.0, 1.0, 0.0, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        quartic_spline_kernel(np.ones(3), np.ones(3))
+
+
+def test_coordinate_axes_mirror():
+    from astro_sph_tools_b200 import CoordinateAxes
+    assert [a.value for a in CoordinateAxes] == [0, 1, 2]
+    assert [str(a) for a in CoordinateAxes] == ["x", "y", "z"]
+    assert CoordinateAxes.from_string(" Y ") is CoordinateAxes.Y
+    with pytest.raises(ValueError):
+        CoordinateAxes.from_string("w")
+    assert CoordinateAxes.X.plane_columns == (1, 2) and CoordinateAxes.Y.plane_columns == (0, 2) and CoordinateAxes.Z.plane_columns == (0, 1)
+
+
+def test_product_never_imports_oracle():
+    """the oracle is test infrastructure: nothing under the package may reference it"""
+    pkg = os.path.join(ROOT, "astro-sph-tools_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "liboracle" not in src, f

@@ -1,0 +1,122 @@
+"""Index work on the CPU: the product's own float64 geometry (csrc/ast_geom.h compiled for the host,
+libastsph_hostgeom.so) must agree BIT FOR BIT with the oracle, and the oracle's fast evaluation must agree with
+its brute-force definition (canonical 1-D ranges, tile membership)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_cloud
+
+CSRC = os.path.join(ROOT, "astro-sph-tools_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def hostgeom():
+    so = os.path.join(CSRC, "libastsph_hostgeom.so")
+    src = [os.path.join(CSRC, f) for f in ("host_geom.cpp", "ast_geom.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in src):
+        subprocess.check_call(["make", "-s", "-C", CSRC, "libastsph_hostgeom.so"])
+    lib = C.CDLL(so)
+    lib.hostgeom_pairs2d.restype = C.c_int64
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def product_bbox_cls(lib, oracle, pos, h, image_size, axis, bounds, small, huge, periodic=False, box=None):
+    n_img, sa, sb = oracle.images(periodic, box)
+    n = len(h)
+    bbox = np.empty((n_img * n, 4), dtype=np.int32); cls = np.empty(n_img * n, dtype=np.uint8)
+    lib.hostgeom_bbox_cls2d(_p(pos), _p(h), C.c_int64(n), C.c_int(axis), C.c_int(image_size[0]), C.c_int(image_size[1]),
+                            *(C.c_double(v) for v in bounds), C.c_int(n_img), _p(sa), _p(sb), C.c_int64(small),
+                            C.c_int64(huge), _p(bbox), _p(cls))
+    return bbox, cls.reshape(n_img, n)
+
+
+def product_pairs(lib, oracle, pos, h, image_size, axis, bounds, small, huge, periodic=False, box=None):
+    n_img, sa, sb = oracle.images(periodic, box)
+    n = len(h)
+    args = [_p(pos), _p(h), C.c_int64(n), C.c_int(axis), C.c_int(image_size[0]), C.c_int(image_size[1]),
+            *(C.c_double(v) for v in bounds), C.c_int(n_img), _p(sa), _p(sb), C.c_int64(small), C.c_int64(huge)]
+    cnt = lib.hostgeom_pairs2d(*args, None, C.c_int64(0))
+    out = np.empty(max(cnt, 1), dtype=np.uint64)
+    lib.hostgeom_pairs2d(*args, _p(out), C.c_int64(cnt))
+    return out[:cnt]
+
+
+def adversarial(seed, n, npix, lo, hi):
+    """particles sitting exactly on sample points, radii that are exact multiples of the pixel size, sub-pixel and
+    huge radii, particles outside the window, non-finite and non-positive h"""
+    rng = np.random.default_rng(seed)
+    d = (hi - lo) / npix
+    pos = rng.uniform(lo - 3 * d, hi + 3 * d, (n, 3))
+    on = rng.random(n) < 0.4
+    pos[on] = lo + np.round((pos[on] - lo) / d) * d                   # exactly on (or next to) sample points
+    h = rng.choice([0.25 * d, 0.5 * d, d, 1.5 * d, 2.0 * d, 7.3 * d, 1e-9 * d, 40 * d], n) * rng.choice([1.0, 1.0, 1.0 + 1e-15, 1.0 - 1e-15], n)
+    h[::17] = 0.0; h[5::29] = -1.0; h[7::31] = np.nan; h[11::37] = np.inf
+    pos[13::41, 0] = np.nan; pos[3::43, 1] = np.inf
+    return np.ascontiguousarray(pos), h
+
+
+CASES = [
+    dict(seed=1, n=4000, npix=(64, 64), bounds=(0.0, 10.0, 0.0, 10.0), axis=2),
+    dict(seed=2, n=4000, npix=(96, 40), bounds=(-3.0, 7.0, 2.0, 5.0), axis=0),
+    dict(seed=3, n=4000, npix=(33, 130), bounds=(1.0, 2.0, 0.0, 10.0), axis=1),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_bbox_fast_equals_brute_definition(oracle, case):
+    pos, h = adversarial(case["seed"], case["n"], case["npix"][0], case["bounds"][0], case["bounds"][1])
+    fast = oracle.bbox2d(pos, h, case["npix"], case["axis"], *case["bounds"])
+    brute = oracle.bbox2d(pos, h, case["npix"], case["axis"], *case["bounds"], brute=True)
+    assert np.array_equal(fast, brute)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("periodic", [False, True])
+def test_product_geometry_bit_exact_vs_oracle(oracle, hostgeom, case, periodic):
+    pos, h = adversarial(case["seed"] + 10, case["n"], case["npix"][0], case["bounds"][0], case["bounds"][1])
+    box = (case["bounds"][1] - case["bounds"][0], case["bounds"][3] - case["bounds"][2]) if periodic else None
+    small, huge = 9, 6
+    o = oracle.bin2d(pos, h, case["npix"], case["axis"], *case["bounds"], tile=32, small_max_px=small, huge_min_tiles=huge,
+                     periodic=periodic, box=box)
+    ob = oracle.bbox2d(pos, h, case["npix"], case["axis"], *case["bounds"], periodic=periodic, box=box)
+    bbox, cls = product_bbox_cls(hostgeom, oracle, pos, h, case["npix"], case["axis"], case["bounds"], small, huge, periodic, box)
+    assert np.array_equal(bbox, ob)
+    assert np.array_equal(cls, o["cls"])
+    assert set(np.unique(cls)) >= {0, 1, 2}
+    pairs = product_pairs(hostgeom, oracle, pos, h, case["npix"], case["axis"], case["bounds"], small, huge, periodic, box)
+    assert np.array_equal(pairs, o["pairs"])
+
+
+def test_tile_membership_fast_equals_brute(oracle):
+    pos, h, _ = random_cloud(5, 1500, h_hi=2.5)
+    kw = dict(tile=32, small_max_px=4, huge_min_tiles=1 << 30)
+    a = oracle.bin2d(pos, h, (200, 200), 2, 0.0, 10.0, 0.0, 10.0, **kw)
+    b = oracle.bin2d(pos, h, (200, 200), 2, 0.0, 10.0, 0.0, 10.0, brute=True, **kw)
+    assert np.array_equal(a["pairs"], b["pairs"]) and len(a["pairs"]) > 3000
+    # culling really removes corner tiles for large circles
+    bb = oracle.bbox2d(pos, h, (200, 200), 2, 0.0, 10.0, 0.0, 10.0)
+    ntile_bbox = ((bb[:, 1] // 32 - bb[:, 0] // 32 + 1) * (bb[:, 3] // 32 - bb[:, 2] // 32 + 1))[a["cls"][0] == 2].sum()
+    assert len(a["pairs"]) <= ntile_bbox
+
+
+def test_sorted_pairs_are_stable_by_key(oracle):
+    pos, h, _ = random_cloud(6, 3000, h_hi=1.0)
+    o = oracle.bin2d(pos, h, (128, 128), 2, 0.0, 10.0, 0.0, 10.0, small_max_px=4)
+    key = (o["pairs"] >> np.uint64(32)).astype(np.int64)
+    order = np.argsort(key, kind="stable")
+    assert np.array_equal(o["sorted"], o["pairs"][order])
+
+
+def test_contributor_count_matches_map_support(oracle):
+    pos, h, prop = random_cloud(7, 800, h_hi=0.8)
+    m = oracle.project2d(pos, h, prop, (50, 50), 2, 0.0, 10.0, 0.0, 10.0)
+    cnt = oracle.contrib_count2d(pos, h, (50, 50), 2, 0.0, 10.0, 0.0, 10.0)
+    assert np.array_equal(cnt > 0, m != 0)
