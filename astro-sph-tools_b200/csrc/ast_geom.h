@@ -68,7 +68,8 @@ AST_HD double radius2(double h)
 // predicate, hence the result does not depend on how the seed was rounded.
 AST_HD bool range1(const Axis1 &a, double p, double h, double R2, int &lo, int &hi)
 {
-    if (!(R2 > 0.0) || !(R2 < INFINITY) || !(fabs(p) < INFINITY)) return false;   // also rejects NaN
+    // h <= 0, NaN or inf never contributes (documented deviation: the reference would use (2h)^2 for h < 0)
+    if (!(h > 0.0) || !(R2 > 0.0) || !(R2 < INFINITY) || !(fabs(p) < INFINITY)) return false;
     double h2 = AST_DMUL(2.0, h);
     double tl = floor(AST_DMUL(AST_DSUB(AST_DSUB(p, h2), a.vmin), a.inv_d));
     double th = ceil(AST_DMUL(AST_DSUB(AST_DADD(p, h2), a.vmin), a.inv_d));

@@ -55,7 +55,8 @@ def gpu_contrib_count(pos, h, image_size, axis, bounds, periodic=False, box=None
     lib = _lib.load()
     p = make_params(len(h), image_size, axis, bounds, periodic=periodic, box=box)
     cnt = torch.empty(image_size, dtype=torch.int32, device="cuda")
-    _lib.check(lib.ast_contrib_count2d(C.byref(p), _lib.ptr(dev(pos)), _lib.ptr(dev(h)), _lib.ptr(cnt), _lib.stream_ptr()))
+    pos_d, h_d = dev(pos), dev(h)          # keep the tensors alive until the kernel has run
+    _lib.check(lib.ast_contrib_count2d(C.byref(p), _lib.ptr(pos_d), _lib.ptr(h_d), _lib.ptr(cnt), _lib.stream_ptr()))
     torch.cuda.synchronize()
     return cnt.cpu().numpy()
 

@@ -34,7 +34,7 @@ def test_bin2d_bit_exact(oracle, case, periodic):
     from gpu_util import gpu_bin2d
     pos, h = adversarial(case["seed"] + 20, case["n"], case["npix"][0], case["bounds"][0], case["bounds"][1])
     box = (case["bounds"][1] - case["bounds"][0], case["bounds"][3] - case["bounds"][2]) if periodic else None
-    small, huge = 9, 6
+    small, huge = 9, 2
     o = oracle.bin2d(pos, h, case["npix"], case["axis"], *case["bounds"], tile=32, small_max_px=small, huge_min_tiles=huge,
                      periodic=periodic, box=box)
     ob = oracle.bbox2d(pos, h, case["npix"], case["axis"], *case["bounds"], periodic=periodic, box=box)

@@ -46,7 +46,7 @@ def test_create_image_drop_in_signature():
     check(img, g["ref_map"])
     img2 = create_image(g["pos"], g["h"], g["prop"], (128, 128), 50, CoordinateAxes.Z, 0.0, 1.0, 0.0, 1.0,
                         kernel_func=quartic_spline_kernel)
-    assert np.array_equal(img, img2)                       # chunk_size does not change the result (reference: PROBE)
+    assert rel_l2(img, img2) < 1e-12                       # chunk_size does not change the result (float64 atomics reorder sums)
     g = load_golden("cloud_axis0")
     img = create_image(g["pos"], g["h"], g["prop"], (64, 64), 50, CoordinateAxes.X, *g["bounds"])
     check(img, g["ref_map"])
@@ -88,7 +88,7 @@ def test_multiple_rounds_small_pair_capacity(oracle):
     from gpu_util import gpu_project
     pos, h, prop = random_cloud(11, 6000, h_hi=1.0)
     ref = oracle.project2d(pos, h, prop, (128, 128), 2, 0.0, 10.0, 0.0, 10.0)
-    m, st = gpu_project(pos, h, prop, (128, 128), 2, (0.0, 10.0, 0.0, 10.0), pair_capacity=5000)
+    m, st = gpu_project(pos, h, prop, (128, 128), 2, (0.0, 10.0, 0.0, 10.0), pair_capacity=2000)
     assert st["n_rounds"] > 3
     check(m, ref)
 
@@ -138,7 +138,7 @@ def test_properties_linearity_permutation(oracle):
     # axis permutation equivalence: projecting along X of (x,y,z) == along Z of (y,z,x)
     mx, _ = gpu_project(pos, h, prop, (96, 96), 0, b)
     mz, _ = gpu_project(np.ascontiguousarray(pos[:, [1, 2, 0]]), h, prop, (96, 96), 2, b)
-    assert np.array_equal(mx, mz)
+    assert rel_l2(mx, mz) < 1e-12                          # only the order of the float64 atomic adds differs
     # sharding: sum of the maps of two halves == map of the whole (linear in particles)
     ma, _ = gpu_project(pos[:2000], h[:2000], prop[:2000], (96, 96), 2, b)
     mb, _ = gpu_project(pos[2000:], h[2000:], prop[2000:], (96, 96), 2, b)
