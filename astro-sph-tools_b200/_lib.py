@@ -41,7 +41,8 @@ class Grid3DParams(C.Structure):
 
 class KnnParams(C.Structure):
     _fields_ = [("n", C.c_int64), ("k", C.c_int32), ("flags", C.c_int32), ("box", C.c_double),
-                ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("cell_target", C.c_double)]
+                ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("cell_target", C.c_double),
+                ("q_begin", C.c_int64), ("q_count", C.c_int64)]
 
 
 class WorkspaceError(RuntimeError):
@@ -52,7 +53,7 @@ _lib = None
 
 # every symbol include/astro_sph_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = ["ast_project2d_workspace_bytes", "ast_project2d", "ast_bin2d", "ast_contrib_count2d", "ast_kernel_eval",
-           "ast_sort_workspace_bytes", "ast_radix_sort_u64", "ast_grid3d_workspace_bytes", "ast_grid3d",
+           "ast_sort_workspace_bytes", "ast_radix_sort_u64", "ast_grid3d_workspace_bytes", "ast_grid3d", "ast_bin3d",
            "ast_knn_workspace_bytes", "ast_knn_h", "ast_last_error", "ast_abi_version", "ast_tile_size",
            "ast_device_sm_count"]
 

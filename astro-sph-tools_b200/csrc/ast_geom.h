@@ -168,6 +168,64 @@ AST_HD int for_each_tile2(const Axis1 &ax, const Axis1 &ay, double pa, double pb
     return cnt;
 }
 
+// ---- 3-D voxel grid: bricks of BRICK^3 voxels, same canonical ranges per axis ----------------------------------
+struct Bin3 {
+    int lo[3], hi[3];      // voxel bbox, inclusive (empty: hi < lo)
+    int b0[3], b1[3];      // brick bbox
+    int cls;
+};
+
+template <int BRICK>
+AST_HD Bin3 classify3(const Axis1 *ax /* [3] */, const double *p /* [3] */, double h, double R2, int64_t small_max_vox,
+                      int64_t huge_min_bricks)
+{
+    Bin3 b;
+    b.cls = CLS_EMPTY;
+    for (int c = 0; c < 3; ++c) { b.lo[c] = 0; b.hi[c] = -1; b.b0[c] = 0; b.b1[c] = -1; }
+    int lo[3], hi[3];
+    for (int c = 0; c < 3; ++c)
+        if (!range1(ax[c], p[c], h, R2, lo[c], hi[c])) return b;
+    int64_t vol = 1, nb = 1;
+    for (int c = 0; c < 3; ++c) {
+        b.lo[c] = lo[c]; b.hi[c] = hi[c];
+        vol *= (int64_t)(hi[c] - lo[c] + 1);
+    }
+    if (vol <= small_max_vox) { b.cls = CLS_SMALL; return b; }
+    for (int c = 0; c < 3; ++c) {
+        b.b0[c] = lo[c] / BRICK; b.b1[c] = hi[c] / BRICK;
+        nb *= (int64_t)(b.b1[c] - b.b0[c] + 1);
+    }
+    b.cls = nb > huge_min_bricks ? CLS_HUGE : CLS_TILED;
+    return b;
+}
+
+// bricks in emit order (bx, by, bz ascending) that hold at least one voxel with (dx^2 + dy^2) + dz^2 < R2
+template <int BRICK, class F>
+AST_HD int for_each_brick3(const Axis1 *ax, const double *p, double R2, const Bin3 &b, int nby, int nbz, F &&f)
+{
+    int cnt = 0;
+    for (int bx = b.b0[0]; bx <= b.b1[0]; ++bx) {
+        int xa = bx * BRICK > b.lo[0] ? bx * BRICK : b.lo[0];
+        int xb = bx * BRICK + BRICK - 1 < b.hi[0] ? bx * BRICK + BRICK - 1 : b.hi[0];
+        double mdx = min_dist2(ax[0], p[0], xa, xb);
+        for (int by = b.b0[1]; by <= b.b1[1]; ++by) {
+            int ya = by * BRICK > b.lo[1] ? by * BRICK : b.lo[1];
+            int yb = by * BRICK + BRICK - 1 < b.hi[1] ? by * BRICK + BRICK - 1 : b.hi[1];
+            double mdxy = AST_DADD(mdx, min_dist2(ax[1], p[1], ya, yb));
+            for (int bz = b.b0[2]; bz <= b.b1[2]; ++bz) {
+                int za = bz * BRICK > b.lo[2] ? bz * BRICK : b.lo[2];
+                int zb = bz * BRICK + BRICK - 1 < b.hi[2] ? bz * BRICK + BRICK - 1 : b.hi[2];
+                double mdz = min_dist2(ax[2], p[2], za, zb);
+                if (AST_DADD(mdxy, mdz) < R2) {
+                    f((uint32_t)((bx * nby + by) * nbz + bz));
+                    ++cnt;
+                }
+            }
+        }
+    }
+    return cnt;
+}
+
 // in-plane columns of the (N,3) position rows: X->(1,2), Y->(0,2), Z->(0,1)  (_pixel_calculations.pyx:20-28)
 AST_HD void plane_columns(int axis, int &a, int &b)
 {

@@ -1,0 +1,515 @@
+// grid3d.cu -- SPH deposition onto a 3-D voxel grid, sm_100a.  EXTENSION named by BASELINE.json (config 4); the
+// reference has no 3-D function.  Rules are the 2-D path's (tools/projections/_pixel_calculations.pyx:11-14,30-34)
+// carried to three axes: sample point = voxel lower corner min + index*delta, contributor iff
+// (dx^2 + dy^2) + dz^2 < (2h)^2 in float64, value = sum A_i W(r, h_i) with a 3-D normalised kernel.
+//
+// Same pipeline as project2d.cu on bricks of 8^3 voxels: bin (+ direct deposit of few-voxel particles with float64
+// atomics) -> scan -> emit (brick key << 32 | particle) -> stable radix sort -> brick ranges -> one CTA per brick:
+// 4 warps, each owning a 4x4x8 column of the brick, 4 voxels (contiguous in z) per thread in registers.
+#include <string.h>
+
+#include "ast_geom.h"
+#include "ast_math.h"
+#include "block_utils.cuh"
+#include "common.cuh"
+#include "scan_sort.cuh"
+
+namespace ast {
+
+constexpr int BRICK = AST_BRICK;
+constexpr int kBin3Threads = 256;
+constexpr int kMaxImg3 = 27;
+constexpr int kAcc3Threads = 128;
+constexpr int kChunk3 = 128;
+
+struct __align__(32) Rec3 {
+    double x, y, z;
+    float h, c;
+};
+static_assert(sizeof(Rec3) == 32, "record is one 32-byte sector");
+
+struct P3 {
+    const double *pos, *h, *prop;
+    double *out;
+    int64_t n;
+    int kernel_id, shape;
+    Axis1 ax[3];
+    int nb[3];                       // bricks per axis
+    int n_img, img_shift;
+    double shift[kMaxImg3][3];
+    int64_t small_max_vox, huge_min_bricks;
+};
+
+template <int SHAPE>
+__device__ __forceinline__ void deposit_small3(const P3 &p, const Bin3 &b, const double *q, double h, double R2, double coef)
+{
+    const double inv_h2 = 1.0 / (h * h);
+    const size_t ny = p.ax[1].n, nz = p.ax[2].n;
+    for (int xi = b.lo[0]; xi <= b.hi[0]; ++xi) {
+        const double dx2 = dist2(p.ax[0], q[0], xi);
+        for (int yi = b.lo[1]; yi <= b.hi[1]; ++yi) {
+            const double dxy = AST_DADD(dx2, dist2(p.ax[1], q[1], yi));
+            double *row = p.out + ((size_t)xi * ny + yi) * nz;
+            for (int zi = b.lo[2]; zi <= b.hi[2]; ++zi) {
+                const double r2 = AST_DADD(dxy, dist2(p.ax[2], q[2], zi));
+                if (r2 < R2) atomicAdd(row + zi, coef * (double)shape_eval<SHAPE>(fast_sqrt((float)(r2 * inv_h2))));
+            }
+        }
+    }
+}
+
+template <int SHAPE, bool DEPOSIT>
+__global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restrict__ rec, uint64_t *__restrict__ block_pairs,
+                                                            uint64_t *__restrict__ block_huge)
+{
+    __shared__ uint32_t red[34];
+    const int64_t i = (int64_t)blockIdx.x * kBin3Threads + threadIdx.x;
+    uint32_t npairs = 0, nhuge = 0;
+    if (i < p.n) {
+        const double x0[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
+        const double h = p.h[i], R2 = radius2(h);
+        bool need_rec = false;
+        for (int m = 0; m < p.n_img; ++m) {
+            const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+            Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
+            if (b.cls == CLS_SMALL) {
+                if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * kernel_norm(p.kernel_id, h));
+            } else if (b.cls == CLS_TILED) {
+                npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
+                need_rec = true;
+            } else if (b.cls == CLS_HUGE) {
+                ++nhuge;
+                need_rec = true;
+            }
+        }
+        if (need_rec && DEPOSIT) {
+            Rec3 r;
+            r.x = x0[0]; r.y = x0[1]; r.z = x0[2];
+            r.h = (float)h;
+            r.c = (float)(p.prop[i] * kernel_norm(p.kernel_id, h));
+            rec[i] = r;
+        }
+    }
+    uint32_t tp = block_sum_u32(npairs, red);
+    uint32_t th = block_sum_u32(nhuge, red);
+    if (threadIdx.x == 0) {
+        block_pairs[blockIdx.x] = tp;
+        block_huge[blockIdx.x] = th;
+    }
+}
+
+__global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_t *__restrict__ pairs_excl,
+                                                             const uint64_t *__restrict__ huge_excl, uint64_t w0, uint64_t w1,
+                                                             uint64_t *__restrict__ pairs, uint64_t *__restrict__ huge,
+                                                             int write_huge, uint64_t huge_capacity)
+{
+    __shared__ uint32_t sm[34];
+    const uint64_t pbase = pairs_excl[blockIdx.x], pnext = pairs_excl[blockIdx.x + 1];
+    const uint64_t hbase = huge_excl[blockIdx.x], hnext = huge_excl[blockIdx.x + 1];
+    const bool any_pairs = pnext > pbase && pnext > w0 && pbase < w1;
+    const bool any_huge = write_huge && hnext > hbase;
+    if (!any_pairs && !any_huge) return;
+    const int64_t i = (int64_t)blockIdx.x * kBin3Threads + threadIdx.x;
+    double x0[3] = { 0, 0, 0 }, h = 0, R2 = 0;
+    uint32_t npairs = 0, nhuge = 0;
+    if (i < p.n) {
+        x0[0] = p.pos[3 * i]; x0[1] = p.pos[3 * i + 1]; x0[2] = p.pos[3 * i + 2];
+        h = p.h[i];
+        R2 = radius2(h);
+        for (int m = 0; m < p.n_img; ++m) {
+            const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+            Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
+            if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
+            else if (b.cls == CLS_HUGE) ++nhuge;
+        }
+    }
+    uint32_t tot;
+    uint64_t g = pbase + block_excl_scan_u32(npairs, sm, &tot);
+    uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
+    if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
+    for (int m = 0; m < p.n_img; ++m) {
+        const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+        Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
+        if (b.cls == CLS_TILED) {
+            for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [&](uint32_t key) {
+                if (g >= w0 && g < w1)
+                    pairs[g - w0] = ((uint64_t)((key << p.img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
+                ++g;
+            });
+        } else if (b.cls == CLS_HUGE) {
+            if (write_huge && gh < huge_capacity) huge[gh] = ((uint64_t)m << 32) | (uint64_t)(uint32_t)i;
+            ++gh;
+        }
+    }
+}
+
+static __global__ void brick_range_kernel(const uint64_t *__restrict__ sorted, int64_t n, int img_shift, uint32_t *__restrict__ tbeg,
+                                          uint32_t *__restrict__ tend)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = (uint32_t)(sorted[i] >> 32) >> img_shift;
+    if (i == 0 || ((uint32_t)(sorted[i - 1] >> 32) >> img_shift) != t) tbeg[t] = (uint32_t)i;
+    if (i == n - 1 || ((uint32_t)(sorted[i + 1] >> 32) >> img_shift) != t) tend[t] = (uint32_t)(i + 1);
+}
+
+struct Acc3 {
+    const uint64_t *sorted;
+    const uint32_t *tbeg, *tend;
+    const uint64_t *huge;
+    uint32_t n_huge;
+    const Rec3 *rec;
+    double *out;
+    double lo[3], d[3], inv_d[3];
+    int n[3], nb[3], img_shift;
+    double shift[kMaxImg3][3];
+};
+
+template <int SHAPE>
+__global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
+{
+    __shared__ float4 sP[kChunk3];      // {ux*sx, uy*sy, uz*sz, c}
+    __shared__ float4 sS[kChunk3];      // {sx, sy, sz, warp mask}
+    __shared__ int s_cnt[4];
+
+    const int brick = blockIdx.x;
+    const uint32_t beg = a.tbeg[brick], cnt = a.tend[brick] - beg;
+    const uint32_t total = cnt + a.n_huge;
+    if (total == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bz = brick % a.nb[2], by = (brick / a.nb[2]) % a.nb[1], bx = brick / (a.nb[2] * a.nb[1]);
+    const int X0 = bx * BRICK, Y0 = by * BRICK, Z0 = bz * BRICK;
+    // warp -> 4x4 column (x,y quadrant), lane -> (lx, ly, z half); 4 voxels contiguous in z per thread
+    const int xl = 4 * (warp >> 1) + (lane >> 3);
+    const int yl = 4 * (warp & 1) + ((lane >> 1) & 3);
+    const int zl = 4 * (lane & 1);
+    const float xf = (float)xl, yf = (float)yl;
+    const float zf0 = (float)zl, zf1 = (float)(zl + 1), zf2 = (float)(zl + 2), zf3 = (float)(zl + 3);
+    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+    double acc64[4] = { 0.0, 0.0, 0.0, 0.0 };
+
+    for (uint32_t base = 0; base < total; base += kChunk3) {
+        const uint32_t j = base + tid;
+        float4 P = make_float4(0.f, 0.f, 0.f, 0.f), S = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t mask = 0;
+        if (j < total) {
+            uint32_t idx, m;
+            if (j < cnt) {
+                const uint64_t e = a.sorted[beg + j];
+                idx = (uint32_t)e;
+                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
+            } else {
+                const uint64_t e = a.huge[j - cnt];
+                idx = (uint32_t)e;
+                m = (uint32_t)(e >> 32);
+            }
+            const Rec3 r = a.rec[idx];
+            const float fx = (float)((r.x + a.shift[m][0] - a.lo[0]) * a.inv_d[0] - (double)X0);
+            const float fy = (float)((r.y + a.shift[m][1] - a.lo[1]) * a.inv_d[1] - (double)Y0);
+            const float fz = (float)((r.z + a.shift[m][2] - a.lo[2]) * a.inv_d[2] - (double)Z0);
+            const double inv_h = 1.0 / (double)r.h;
+            const float sx = (float)(a.d[0] * inv_h), sy = (float)(a.d[1] * inv_h), sz = (float)(a.d[2] * inv_h);
+            P = make_float4(fx * sx, fy * sy, fz * sz, r.c);
+            const float ddz = fmaxf(fmaxf(-fz, fz - 7.f), 0.f) * sz;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float lox = 4.f * (float)(w >> 1), loy = 4.f * (float)(w & 1);
+                const float ddx = fmaxf(fmaxf(lox - fx, fx - (lox + 3.f)), 0.f) * sx;
+                const float ddy = fmaxf(fmaxf(loy - fy, fy - (loy + 3.f)), 0.f) * sy;
+                if (ddx * ddx + ddy * ddy + ddz * ddz < 4.0001f) mask |= 1u << w;
+            }
+            S = make_float4(sx, sy, sz, __uint_as_float(mask));
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, mask != 0);
+        __syncthreads();
+        if (lane == 0) s_cnt[warp] = __popc(ball);
+        __syncthreads();
+        int off = 0, nc = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int c = s_cnt[w];
+            off += w < warp ? c : 0;
+            nc += c;
+        }
+        if (mask != 0) {
+            const int dst = off + __popc(ball & ((1u << lane) - 1u));
+            sP[dst] = P;
+            sS[dst] = S;
+        }
+        __syncthreads();
+        for (int e = 0; e < nc; ++e) {
+            const float4 s = sS[e];
+            if (!((__float_as_uint(s.w) >> warp) & 1u)) continue;
+            const float4 q = sP[e];
+            const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
+            const float axy = fmaf(by2, by2, ax * ax);
+            const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
+            acc[0] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c0, c0, axy))), acc[0]);
+            acc[1] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c1, c1, axy))), acc[1]);
+            acc[2] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c2, c2, axy))), acc[2]);
+            acc[3] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c3, c3, axy))), acc[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc64[k] += (double)acc[k]; acc[k] = 0.f; }
+    }
+    const int xi = X0 + xl, yi = Y0 + yl;
+    if (xi < a.n[0] && yi < a.n[1]) {
+        double *row = a.out + ((size_t)xi * a.n[1] + yi) * a.n[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (Z0 + zl + k < a.n[2]) row[Z0 + zl + k] += acc64[k];
+    }
+}
+
+__global__ void bbox_cls3_kernel(P3 p, int32_t *__restrict__ bbox, uint8_t *__restrict__ cls)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const double x0[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
+    const double h = p.h[i], R2 = radius2(h);
+    for (int m = 0; m < p.n_img; ++m) {
+        const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+        Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
+        const int64_t j = (int64_t)m * p.n + i;
+        if (bbox)
+            for (int c = 0; c < 3; ++c) { bbox[6 * j + 2 * c] = b.lo[c]; bbox[6 * j + 2 * c + 1] = b.hi[c]; }
+        if (cls) cls[j] = (uint8_t)b.cls;
+    }
+}
+
+constexpr int64_t kDefaultSmallMaxVox = 27;
+constexpr int64_t kDefaultHugeMinBricks = 512;
+
+struct Layout3 {
+    int64_t nb, nbricks, pair_cap, huge_cap;
+    uint64_t *block_pairs, *block_huge;
+    Rec3 *rec;
+    uint64_t *pairs_a, *pairs_b, *huge;
+    uint32_t *tbeg, *tend;
+    void *sort_ws;
+    size_t bytes;
+};
+
+static int validate3(const ast_grid3d_params *p)
+{
+    AST_REQUIRE(p != nullptr, "params is null");
+    AST_REQUIRE(p->n >= 0 && p->n < (int64_t)0xffffffffll, "n out of range");
+    AST_REQUIRE(p->nx > 0 && p->ny > 0 && p->nz > 0, "grid size must be positive");
+    const int64_t nbr = (int64_t)((p->nx + BRICK - 1) / BRICK) * ((p->ny + BRICK - 1) / BRICK) * ((p->nz + BRICK - 1) / BRICK);
+    AST_REQUIRE(nbr < (1ll << 26), "grid too large (more than 2^26 bricks)");
+    AST_REQUIRE(kernel_valid(p->kernel_id), "unknown kernel id %d", p->kernel_id);
+    for (int c = 0; c < 3; ++c) AST_REQUIRE(p->hi[c] > p->lo[c], "empty or inverted grid bounds");
+    if (p->flags & AST_FLAG_PERIODIC)
+        for (int c = 0; c < 3; ++c) AST_REQUIRE(p->box[c] > 0, "periodic gridding needs box[0..2] > 0");
+    AST_REQUIRE(p->pair_capacity >= 0 && p->pair_capacity < (1ll << 32), "pair_capacity out of range");
+    AST_REQUIRE(p->huge_capacity >= 0 && p->huge_capacity < (1ll << 32), "huge_capacity out of range");
+    return AST_OK;
+}
+
+static Layout3 layout3(const ast_grid3d_params *p, void *ws)
+{
+    Layout3 L;
+    L.nb = (p->n + kBin3Threads - 1) / kBin3Threads;
+    if (L.nb < 1) L.nb = 1;
+    L.nbricks = (int64_t)((p->nx + BRICK - 1) / BRICK) * ((p->ny + BRICK - 1) / BRICK) * ((p->nz + BRICK - 1) / BRICK);
+    L.pair_cap = p->pair_capacity > 0 ? p->pair_capacity : 1;
+    L.huge_cap = p->huge_capacity > 0 ? p->huge_capacity : 1;
+    Carver c(ws);
+    L.block_pairs = c.take<uint64_t>(L.nb + 1);
+    L.block_huge = c.take<uint64_t>(L.nb + 1);
+    L.rec = c.take<Rec3>(p->n > 0 ? p->n : 1);
+    L.pairs_a = c.take<uint64_t>(L.pair_cap);
+    L.pairs_b = c.take<uint64_t>(L.pair_cap);
+    L.huge = c.take<uint64_t>(L.huge_cap);
+    L.tbeg = c.take<uint32_t>(L.nbricks);
+    L.tend = c.take<uint32_t>(L.nbricks);
+    L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
+    L.bytes = c.bytes();
+    return L;
+}
+
+static P3 make_p3(const ast_grid3d_params *p, const double *pos, const double *h, const double *prop, double *out)
+{
+    P3 a;
+    a.pos = pos; a.h = h; a.prop = prop; a.out = out;
+    a.n = p->n;
+    a.kernel_id = p->kernel_id;
+    a.shape = kernel_shape(p->kernel_id);
+    const int n3[3] = { p->nx, p->ny, p->nz };
+    for (int c = 0; c < 3; ++c) {
+        a.ax[c] = make_axis(p->lo[c], p->hi[c], n3[c]);
+        a.nb[c] = (n3[c] + BRICK - 1) / BRICK;
+    }
+    const bool per = (p->flags & AST_FLAG_PERIODIC) != 0;
+    a.n_img = per ? 27 : 1;
+    a.img_shift = per ? 5 : 0;
+    for (int m = 0; m < kMaxImg3; ++m) {            // image m = 9*(ia+1) + 3*(ib+1) + (ic+1)
+        a.shift[m][0] = per ? (double)(m / 9 - 1) * p->box[0] : 0.0;
+        a.shift[m][1] = per ? (double)((m / 3) % 3 - 1) * p->box[1] : 0.0;
+        a.shift[m][2] = per ? (double)(m % 3 - 1) * p->box[2] : 0.0;
+    }
+    a.small_max_vox = p->small_max_vox >= 0 ? p->small_max_vox : kDefaultSmallMaxVox;
+    a.huge_min_bricks = p->huge_min_bricks >= 0 ? p->huge_min_bricks : kDefaultHugeMinBricks;
+    return a;
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+extern "C" int ast_grid3d_workspace_bytes(const ast_grid3d_params *p, size_t *bytes)
+{
+    int rc = validate3(p);
+    if (rc) return rc;
+    AST_REQUIRE(bytes != nullptr, "bytes is null");
+    *bytes = layout3(p, nullptr).bytes;
+    return AST_OK;
+}
+
+extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const double *h, const double *prop, double *out,
+                          void *workspace, size_t workspace_bytes, void *stream, ast_project2d_stats *stats)
+{
+    int rc = validate3(p);
+    if (rc) return rc;
+    AST_REQUIRE(out != nullptr, "out is null");
+    AST_REQUIRE(p->n == 0 || (pos && h && prop), "null input pointer");
+    Layout3 L = layout3(p, workspace);
+    if (workspace == nullptr || workspace_bytes < L.bytes) {
+        set_error("workspace too small: need %zu bytes, have %zu", L.bytes, workspace_bytes);
+        return AST_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool timing = (p->flags & AST_FLAG_TIMING) != 0;
+    StageTimer tm(timing, s), tk(timing, s);
+    ast_project2d_stats st;
+    memset(&st, 0, sizeof st);
+    P3 a = make_p3(p, pos, h, prop, out);
+    const size_t nvox = (size_t)p->nx * p->ny * p->nz;
+    tm.begin(7);
+    tk.begin(6);
+    if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * nvox, s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    tk.end();
+    uint64_t totals[2] = { 0, 0 };
+    if (p->n > 0) {
+        tk.begin(0);
+        if (a.shape == SHAPE_CUBIC) bin3_kernel<SHAPE_CUBIC, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        else bin3_kernel<SHAPE_WENDLAND, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        tk.end();
+        tk.begin(1);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
+        tk.end();
+        st.n_launches += 3;
+        AST_CUDA_TRY(cudaGetLastError());
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    st.n_pairs = (int64_t)totals[0];
+    st.n_huge = (int64_t)totals[1];
+    if (totals[1] > (uint64_t)L.huge_cap || (totals[0] > 0 && p->pair_capacity <= 0)) {
+        set_error("capacity too small: need %llu huge entries (have %lld) and a positive pair_capacity",
+                  (unsigned long long)totals[1], (long long)L.huge_cap);
+        if (stats) *stats = st;
+        return AST_EWORKSPACE;
+    }
+    if (totals[0] + totals[1] > 0) {
+        const uint64_t cap = (uint64_t)L.pair_cap;
+        const int64_t rounds = totals[0] ? (int64_t)((totals[0] + cap - 1) / cap) : 1;
+        const int key_bits = ceil_log2_u64((uint64_t)L.nbricks) + a.img_shift;
+        Acc3 c;
+        c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
+        for (int k = 0; k < 3; ++k) {
+            c.lo[k] = a.ax[k].vmin; c.d[k] = a.ax[k].d; c.inv_d[k] = a.ax[k].inv_d; c.n[k] = a.ax[k].n; c.nb[k] = a.nb[k];
+        }
+        c.img_shift = a.img_shift;
+        memcpy(c.shift, a.shift, sizeof c.shift);
+        for (int64_t r = 0; r < rounds; ++r) {
+            const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
+            const int64_t nw = (int64_t)(w1 - w0);
+            tk.begin(2);
+            emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, w0, w1, L.pairs_a, L.huge, r == 0,
+                                                                (uint64_t)L.huge_cap);
+            tk.end();
+            int in_b = 0, nl = 0;
+            tk.begin(3);
+            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32, key_bits, L.sort_ws, s, &in_b, &nl));
+            tk.end();
+            tk.begin(4);
+            AST_CUDA_TRY(cudaMemsetAsync(L.tbeg, 0, sizeof(uint32_t) * L.nbricks, s));
+            AST_CUDA_TRY(cudaMemsetAsync(L.tend, 0, sizeof(uint32_t) * L.nbricks, s));
+            c.sorted = in_b ? L.pairs_b : L.pairs_a;
+            if (nw > 0) brick_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
+            tk.end();
+            c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
+            tk.begin(5);
+            if (a.shape == SHAPE_CUBIC) brick_accum_kernel<SHAPE_CUBIC><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
+            else brick_accum_kernel<SHAPE_WENDLAND><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
+            tk.end();
+            st.n_launches += 3 + nl;
+            AST_CUDA_TRY(cudaGetLastError());
+        }
+        st.n_rounds = rounds;
+    }
+    tm.end();
+    if (timing) {
+        float total_ms[8];
+        tk.collect(st.stage_ms, 8);
+        tm.collect(total_ms, 8);
+        st.stage_ms[7] = total_ms[7];
+    }
+    if (stats) *stats = st;
+    return AST_OK;
+}
+
+extern "C" int ast_bin3d(const ast_grid3d_params *p, const double *pos, const double *h, int32_t *bbox, uint8_t *cls,
+                         uint64_t *pairs_sorted, uint64_t *huge, int64_t *counts, void *workspace, size_t workspace_bytes,
+                         void *stream)
+{
+    int rc = validate3(p);
+    if (rc) return rc;
+    AST_REQUIRE(p->n == 0 || (pos && h), "null input pointer");
+    Layout3 L = layout3(p, workspace);
+    if (workspace == nullptr || workspace_bytes < L.bytes) {
+        set_error("workspace too small: need %zu bytes, have %zu", L.bytes, workspace_bytes);
+        return AST_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    P3 a = make_p3(p, pos, h, nullptr, nullptr);
+    uint64_t totals[2] = { 0, 0 };
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    if (p->n > 0) {
+        if (bbox || cls) bbox_cls3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, bbox, cls);
+        bin3_kernel<SHAPE_CUBIC, false><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
+        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
+        AST_CUDA_TRY(cudaGetLastError());
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (counts) { counts[0] = (int64_t)totals[0]; counts[1] = (int64_t)totals[1]; }
+    if (totals[0] > (uint64_t)p->pair_capacity || totals[1] > (uint64_t)p->huge_capacity) {
+        set_error("capacity too small: need %llu pairs and %llu huge entries", (unsigned long long)totals[0],
+                  (unsigned long long)totals[1]);
+        return AST_EWORKSPACE;
+    }
+    if (totals[0] + totals[1] > 0) {
+        emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, totals[0], L.pairs_a, L.huge, 1,
+                                                            (uint64_t)L.huge_cap);
+        AST_CUDA_TRY(cudaGetLastError());
+        if (huge && totals[1]) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * totals[1], cudaMemcpyDeviceToDevice, s));
+        if (pairs_sorted && totals[0]) {
+            int in_b = 0;
+            const int key_bits = ceil_log2_u64((uint64_t)L.nbricks) + a.img_shift;
+            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, (int64_t)totals[0], 32, key_bits, L.sort_ws, s, &in_b));
+            AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? L.pairs_b : L.pairs_a, sizeof(uint64_t) * totals[0],
+                                         cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    AST_CUDA_TRY(cudaStreamSynchronize(s));
+    return AST_OK;
+}

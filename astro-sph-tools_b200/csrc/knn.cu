@@ -1,0 +1,323 @@
+// knn.cu -- smoothing lengths by k nearest neighbours on a cell-linked list, sm_100a.
+//
+// Replaces the KDTree branch of SnapshotSWIFT.get_smoothing_lengths (io/SWIFT/_SnapshotSWIFT.py:62-83):
+//   h_i = K-th smallest distance from particle i to all particles, i itself included,
+// with scipy.spatial.cKDTree's float64 arithmetic so that distances are BIT-EQUAL to the reference's:
+//   d = sqrt((dx*dx + dy*dy) + dz*dz), no FMA; periodic (boxsize): each delta is first wrapped by -+box when
+//   |delta| > box/2  (SURVEY 8(a) A7).
+//
+//   1. cell key per particle -> (key << 32 | particle) -> stable radix sort (scan_sort.cuh)
+//   2. gather positions into cell order (SoA), first/last particle of every cell
+//   3. one thread per query: visit cells ring by ring (Chebyshev distance 0,1,2,...), keep the K smallest squared
+//      distances in a max-heap, stop when the K-th is closer than anything that can still be outside the explored cube.
+// Multi-GPU: positions are replicated (1024^3 x 24 B = 25.8 GB fits every 180 GB GPU), each rank answers the
+// queries [q_begin, q_begin + q_count).
+#include <string.h>
+
+#include "ast_geom.h"
+#include "common.cuh"
+#include "scan_sort.cuh"
+
+namespace ast {
+
+struct KnnGrid {
+    double lo[3], inv_cs[3], cs[3];
+    double box, half_box;        // periodic if box > 0
+    int G;
+};
+
+struct KnnArgs {
+    KnnGrid g;
+    const double *xs, *ys, *zs;  // cell order
+    const uint32_t *sidx;        // cell order -> original index
+    const uint32_t *cbeg, *cend;
+    const uint32_t *qlist;       // nullable: sorted positions of the queries
+    int64_t nq, q_begin;
+    int k;
+    double *h_out;
+    int32_t *idx_out;
+    double *dist_out;
+};
+
+__host__ __device__ __forceinline__ int cell_coord(const KnnGrid &g, double x, int c)
+{
+    double t = floor((x - g.lo[c]) * g.inv_cs[c]);
+    int i = t < 0.0 ? 0 : (t > (double)(g.G - 1) ? g.G - 1 : (int)t);
+    return i;
+}
+
+__global__ void knn_key_kernel(const double *__restrict__ pos, int64_t n, KnnGrid g, uint64_t *__restrict__ elems)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = cell_coord(g, pos[3 * i], 0), cy = cell_coord(g, pos[3 * i + 1], 1), cz = cell_coord(g, pos[3 * i + 2], 2);
+    const uint32_t key = ((uint32_t)cx * g.G + cy) * g.G + cz;
+    elems[i] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)i;
+}
+
+__global__ void knn_gather_kernel(const double *__restrict__ pos, const uint64_t *__restrict__ sorted, int64_t n,
+                                  double *__restrict__ xs, double *__restrict__ ys, double *__restrict__ zs,
+                                  uint32_t *__restrict__ sidx, uint32_t *__restrict__ cbeg, uint32_t *__restrict__ cend,
+                                  int64_t q_begin, int64_t q_end, uint32_t *__restrict__ qflag)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint64_t e = sorted[s];
+    const uint32_t i = (uint32_t)e, key = (uint32_t)(e >> 32);
+    xs[s] = pos[3 * (int64_t)i];
+    ys[s] = pos[3 * (int64_t)i + 1];
+    zs[s] = pos[3 * (int64_t)i + 2];
+    sidx[s] = i;
+    if (s == 0 || (uint32_t)(sorted[s - 1] >> 32) != key) cbeg[key] = (uint32_t)s;
+    if (s == n - 1 || (uint32_t)(sorted[s + 1] >> 32) != key) cend[key] = (uint32_t)(s + 1);
+    if (qflag) qflag[s] = ((int64_t)i >= q_begin && (int64_t)i < q_end) ? 1u : 0u;
+}
+
+__global__ void knn_compact_kernel(const uint32_t *__restrict__ qexcl, const uint32_t *__restrict__ sidx, int64_t n, int64_t q_begin,
+                                   int64_t q_end, uint32_t *__restrict__ qlist)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int64_t i = sidx[s];
+    if (i >= q_begin && i < q_end) qlist[qexcl[s]] = (uint32_t)s;
+}
+
+// max-heap on (d2, idx): root = current K-th smallest
+template <int KCAP, bool WANT_IDX>
+struct Heap {
+    double d[KCAP];
+    uint32_t id[WANT_IDX ? KCAP : 1];
+    int k;
+    __device__ __forceinline__ bool less(double d2, uint32_t j, double e2, uint32_t l) const
+    {
+        return WANT_IDX ? (d2 < e2 || (d2 == e2 && j < l)) : (d2 < e2);
+    }
+    __device__ __forceinline__ void replace_root(double d2, uint32_t j)
+    {
+        int p = 0;
+        for (;;) {
+            int c = 2 * p + 1;
+            if (c >= k) break;
+            if (c + 1 < k && less(d[c], WANT_IDX ? id[c] : 0u, d[c + 1], WANT_IDX ? id[c + 1] : 0u)) ++c;   // larger child
+            if (!less(d2, j, d[c], WANT_IDX ? id[c] : 0u)) break;
+            d[p] = d[c];
+            if (WANT_IDX) id[p] = id[c];
+            p = c;
+        }
+        d[p] = d2;
+        if (WANT_IDX) id[p] = j;
+    }
+};
+
+template <int KCAP, bool WANT_IDX>
+__global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nq) return;
+    const int64_t s = a.qlist ? (int64_t)a.qlist[t] : t;
+    const double x = a.xs[s], y = a.ys[s], z = a.zs[s];
+    const KnnGrid &g = a.g;
+    const int G = g.G;
+    const bool per = g.box > 0.0;
+    const int qc[3] = { cell_coord(g, x, 0), cell_coord(g, y, 1), cell_coord(g, z, 2) };
+    const double xq[3] = { x, y, z };
+
+    Heap<KCAP, WANT_IDX> hp;
+    hp.k = a.k;
+    for (int i = 0; i < a.k; ++i) {
+        hp.d[i] = INFINITY;
+        if (WANT_IDX) hp.id[i] = 0xffffffffu;
+    }
+
+    for (int ring = 0;; ++ring) {
+        for (int ox = -ring; ox <= ring; ++ox) {
+            int cx = qc[0] + ox;
+            if (per) { if (2 * abs(ox) > G || (2 * abs(ox) == G && ox < 0)) continue; cx = (cx % G + G) % G; }
+            else if (cx < 0 || cx >= G) continue;
+            for (int oy = -ring; oy <= ring; ++oy) {
+                int cy = qc[1] + oy;
+                if (per) { if (2 * abs(oy) > G || (2 * abs(oy) == G && oy < 0)) continue; cy = (cy % G + G) % G; }
+                else if (cy < 0 || cy >= G) continue;
+                const bool inner = abs(ox) < ring && abs(oy) < ring;
+                for (int oz = -ring; oz <= ring; oz += (inner && ring > 0) ? 2 * ring : 1) {   // shell only
+                    int cz = qc[2] + oz;
+                    if (per) { if (2 * abs(oz) > G || (2 * abs(oz) == G && oz < 0)) continue; cz = (cz % G + G) % G; }
+                    else if (cz < 0 || cz >= G) continue;
+                    const uint32_t c = ((uint32_t)cx * G + cy) * G + cz;
+                    const uint32_t jb = a.cbeg[c], je = a.cend[c];
+                    for (uint32_t j = jb; j < je; ++j) {
+                        double ex = a.xs[j] - x, ey = a.ys[j] - y, ez = a.zs[j] - z;
+                        if (per) {
+                            if (ex < -g.half_box) ex += g.box; else if (ex > g.half_box) ex -= g.box;
+                            if (ey < -g.half_box) ey += g.box; else if (ey > g.half_box) ey -= g.box;
+                            if (ez < -g.half_box) ez += g.box; else if (ez > g.half_box) ez -= g.box;
+                        }
+                        const double d2 = AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez));
+                        const uint32_t oj = WANT_IDX ? a.sidx[j] : 0u;
+                        if (hp.less(d2, oj, hp.d[0], WANT_IDX ? hp.id[0] : 0u)) hp.replace_root(d2, oj);
+                    }
+                }
+            }
+        }
+        // smallest possible distance to anything outside the explored cube of cells
+        double dmin = INFINITY;
+        bool all = true;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double frac = xq[c] - (g.lo[c] + (double)qc[c] * g.cs[c]);
+            bool lo_open, hi_open;
+            if (per) lo_open = hi_open = (2 * ring + 1 < G);
+            else { lo_open = qc[c] - ring > 0; hi_open = qc[c] + ring < G - 1; }
+            if (lo_open) dmin = fmin(dmin, frac + (double)ring * g.cs[c]);
+            if (hi_open) dmin = fmin(dmin, (g.cs[c] - frac) + (double)ring * g.cs[c]);
+            all = all && !lo_open && !hi_open;
+        }
+        if (all) break;
+        const double safe = dmin - 1e-9 * g.cs[0];
+        if (safe > 0.0 && hp.d[0] < safe * safe) break;
+    }
+
+    const int64_t row = (int64_t)a.sidx[s] - a.q_begin;
+    a.h_out[row] = sqrt(hp.d[0]);
+    if (WANT_IDX) {
+        // heap-sort in place: ascending (d2, idx)
+        const int k = a.k;
+        for (int end = k - 1; end > 0; --end) {
+            const double dd = hp.d[end];
+            const uint32_t ii = hp.id[end];
+            hp.d[end] = hp.d[0];
+            hp.id[end] = hp.id[0];
+            hp.k = end;
+            hp.replace_root(dd, ii);
+        }
+        for (int i = 0; i < k; ++i) {
+            if (a.idx_out) a.idx_out[row * k + i] = hp.d[i] < INFINITY ? (int32_t)hp.id[i] : -1;
+            if (a.dist_out) a.dist_out[row * k + i] = sqrt(hp.d[i]);
+        }
+    }
+}
+
+struct KnnLayout {
+    int G;
+    int64_t ncell, nq;
+    uint64_t *ea, *eb;
+    double *xs, *ys, *zs;
+    uint32_t *sidx, *cbeg, *cend, *qflag, *qlist, *scan_tmp;
+    void *sort_ws;
+    size_t bytes;
+};
+
+static int knn_validate(const ast_knn_params *p)
+{
+    AST_REQUIRE(p != nullptr, "params is null");
+    AST_REQUIRE(p->n >= 0 && p->n < (1ll << 31), "n out of range");
+    AST_REQUIRE(p->k >= 1 && p->k <= 128, "k = %d not in [1, 128]", p->k);
+    AST_REQUIRE(p->q_begin >= 0 && p->q_begin + (p->q_count > 0 ? p->q_count : 0) <= p->n, "query range outside [0, n)");
+    if (!(p->box > 0.0))
+        for (int c = 0; c < 3; ++c) AST_REQUIRE(p->hi[c] >= p->lo[c], "open box needs lo <= hi (extent of the positions)");
+    return AST_OK;
+}
+
+static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
+{
+    KnnLayout L;
+    const double m = p->cell_target > 0 ? p->cell_target : (p->k / 3.0 > 2.0 ? p->k / 3.0 : 2.0);
+    double g = floor(cbrt((double)(p->n > 0 ? p->n : 1) / m));
+    L.G = g < 1 ? 1 : (g > 1000 ? 1000 : (int)g);
+    L.ncell = (int64_t)L.G * L.G * L.G;
+    const int64_t n = p->n > 0 ? p->n : 1;
+    L.nq = p->q_count > 0 ? p->q_count : p->n;
+    Carver c(ws);
+    L.ea = c.take<uint64_t>(n);
+    L.eb = c.take<uint64_t>(n);
+    L.xs = c.take<double>(n);
+    L.ys = c.take<double>(n);
+    L.zs = c.take<double>(n);
+    L.sidx = c.take<uint32_t>(n);
+    L.cbeg = c.take<uint32_t>(L.ncell);
+    L.cend = c.take<uint32_t>(L.ncell);
+    L.qflag = c.take<uint32_t>(n);
+    L.qlist = c.take<uint32_t>(n);
+    L.scan_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(n));
+    L.sort_ws = c.take<char>(sort_workspace_bytes(n));
+    L.bytes = c.bytes();
+    return L;
+}
+
+template <int KCAP>
+static void launch_query(const KnnArgs &a, bool want_idx, cudaStream_t s)
+{
+    const unsigned nb = (unsigned)((a.nq + 127) / 128);
+    if (want_idx) knn_query_kernel<KCAP, true><<<nb, 128, 0, s>>>(a);
+    else knn_query_kernel<KCAP, false><<<nb, 128, 0, s>>>(a);
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+extern "C" int ast_knn_workspace_bytes(const ast_knn_params *p, size_t *bytes)
+{
+    int rc = knn_validate(p);
+    if (rc) return rc;
+    AST_REQUIRE(bytes != nullptr, "bytes is null");
+    *bytes = knn_layout(p, nullptr).bytes;
+    return AST_OK;
+}
+
+extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_out, int32_t *idx_out, double *dist_out,
+                         void *workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = knn_validate(p);
+    if (rc) return rc;
+    if (p->n == 0) return AST_OK;
+    AST_REQUIRE(pos && h_out, "null pointer");
+    KnnLayout L = knn_layout(p, workspace);
+    if (!workspace || workspace_bytes < L.bytes) {
+        set_error("workspace too small: need %zu bytes, have %zu", L.bytes, workspace_bytes);
+        return AST_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    KnnGrid g;
+    g.G = L.G;
+    g.box = p->box > 0.0 ? p->box : 0.0;
+    g.half_box = 0.5 * g.box;
+    for (int c = 0; c < 3; ++c) {
+        const double lo = p->box > 0.0 ? 0.0 : p->lo[c];
+        double ext = p->box > 0.0 ? p->box : (p->hi[c] - p->lo[c]);
+        if (!(ext > 0.0)) ext = 1.0;                       // degenerate axis: every particle lands in cell 0
+        g.lo[c] = lo;
+        g.cs[c] = ext / (double)L.G;
+        g.inv_cs[c] = (double)L.G / ext;
+    }
+    const int64_t n = p->n;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    knn_key_kernel<<<nb, 256, 0, s>>>(pos, n, g, L.ea);
+    int in_b = 0;
+    AST_CUDA_TRY(radix_sort_u64(L.ea, L.eb, n, 32, ceil_log2_u64((uint64_t)L.ncell), L.sort_ws, s, &in_b));
+    const uint64_t *sorted = in_b ? L.eb : L.ea;
+    AST_CUDA_TRY(cudaMemsetAsync(L.cbeg, 0, sizeof(uint32_t) * L.ncell, s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.cend, 0, sizeof(uint32_t) * L.ncell, s));
+    const bool subset = p->q_count > 0 && p->q_count < n;
+    const int64_t q_begin = subset ? p->q_begin : 0, q_end = subset ? p->q_begin + p->q_count : n;
+    knn_gather_kernel<<<nb, 256, 0, s>>>(pos, sorted, n, L.xs, L.ys, L.zs, L.sidx, L.cbeg, L.cend, q_begin, q_end,
+                                         subset ? L.qflag : nullptr);
+    if (subset) {
+        AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n, L.scan_tmp, nullptr, s));
+        knn_compact_kernel<<<nb, 256, 0, s>>>(L.qflag, L.sidx, n, q_begin, q_end, L.qlist);
+    }
+    KnnArgs a;
+    a.g = g;
+    a.xs = L.xs; a.ys = L.ys; a.zs = L.zs; a.sidx = L.sidx; a.cbeg = L.cbeg; a.cend = L.cend;
+    a.qlist = subset ? L.qlist : nullptr;
+    a.nq = q_end - q_begin;
+    a.q_begin = q_begin;
+    a.k = p->k;
+    a.h_out = h_out; a.idx_out = idx_out; a.dist_out = dist_out;
+    const bool want = idx_out != nullptr || dist_out != nullptr;
+    if (p->k <= 32) launch_query<32>(a, want, s);
+    else if (p->k <= 64) launch_query<64>(a, want, s);
+    else launch_query<128>(a, want, s);
+    AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
+}

@@ -68,10 +68,97 @@ __global__ void __launch_bounds__(kScanThreads) scan_exclusive_kernel(T *data, i
     if (tid == 0 && total_out) *total_out = carry_s;
 }
 
+// ---- multi-block exclusive scan: per-block sums -> scan of the sums (single block) -> per-block scan + base.
+// One block handles kScanTile consecutive elements.
+constexpr int kScanTile = kScanThreads * kScanItems;      // 4096
+
 template <class T>
-inline cudaError_t scan_exclusive(T *data, int64_t n, T *total_out, cudaStream_t s)
+__device__ __forceinline__ T block_reduce_sum(T v, T *smem32)
 {
-    scan_exclusive_kernel<T><<<1, kScanThreads, 0, s>>>(data, n, total_out);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) smem32[warp] = v;
+    __syncthreads();
+    T t = (threadIdx.x < (blockDim.x >> 5)) ? smem32[threadIdx.x] : (T)0;
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    return t;                                            // valid in thread 0
+}
+
+template <class T>
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(const T *__restrict__ data, int64_t n, T *__restrict__ sums)
+{
+    __shared__ T sm[32];
+    const int64_t i0 = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) s += (i0 + k < n) ? data[i0 + k] : (T)0;
+    T t = block_reduce_sum<T>(s, sm);
+    if (threadIdx.x == 0) sums[blockIdx.x] = t;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(T *__restrict__ data, int64_t n, const T *__restrict__ base)
+{
+    __shared__ T warp_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * kScanTile + (int64_t)tid * kScanItems;
+    T v[kScanItems];
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (i0 + k < n) ? data[i0 + k] : (T)0;
+        s += v[k];
+    }
+    T inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = warp_sum[lane];
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_sum[lane] = winc - w;
+    }
+    __syncthreads();
+    T excl = base[blockIdx.x] + warp_sum[warp] + (inc - s);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (i0 + k < n) data[i0 + k] = excl;
+        excl += v[k];
+    }
+}
+
+inline int64_t scan_num_blocks(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
+template <class T>
+inline size_t scan_workspace_bytes(int64_t n) { return (size_t)(scan_num_blocks(n > 0 ? n : 1) + 1) * sizeof(T); }
+
+// exclusive scan of data[0..n) in place; tmp: scan_workspace_bytes<T>(n); total_out (device, nullable) = sum of all
+template <class T>
+inline cudaError_t scan_exclusive(T *data, int64_t n, T *tmp, T *total_out, cudaStream_t s, int *launches = nullptr)
+{
+    if (n <= 0) return cudaSuccess;
+    if (n <= 2 * kScanTile) {
+        scan_exclusive_kernel<T><<<1, kScanThreads, 0, s>>>(data, n, total_out);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    const int64_t nb = scan_num_blocks(n);
+    scan_block_sums_kernel<T><<<(unsigned)nb, kScanThreads, 0, s>>>(data, n, tmp);
+    scan_exclusive_kernel<T><<<1, kScanThreads, 0, s>>>(tmp, nb, total_out);
+    scan_apply_kernel<T><<<(unsigned)nb, kScanThreads, 0, s>>>(data, n, tmp);
+    if (launches) *launches += 3;
     return cudaGetLastError();
 }
 
@@ -82,12 +169,15 @@ constexpr int kSortBlockItems = kSortWarps * kSortWarpItems;   // 8192
 constexpr int kRadix = 256;
 
 inline int64_t sort_num_blocks(int64_t n) { return (n + kSortBlockItems - 1) / kSortBlockItems; }
+inline size_t sort_table_entries(int64_t n) { return (size_t)sort_num_blocks(n > 0 ? n : 1) * kRadix; }
 inline size_t sort_workspace_bytes(int64_t n)
 {
-    return ((size_t)sort_num_blocks(n > 0 ? n : 1) * kRadix + 64) * sizeof(uint32_t);
+    size_t t = (sort_table_entries(n) + 64) * sizeof(uint32_t);
+    t = (t + 255) / 256 * 256;
+    return t + scan_workspace_bytes<uint32_t>((int64_t)sort_table_entries(n));
 }
 
-__global__ void __launch_bounds__(kSortWarps * 32)
+static __global__ void __launch_bounds__(kSortWarps * 32)
 sort_hist_kernel(const uint64_t *__restrict__ in, int64_t n, int shift, uint32_t mask, uint32_t *__restrict__ table,
                  int64_t nblocks)
 {
@@ -109,7 +199,7 @@ sort_hist_kernel(const uint64_t *__restrict__ in, int64_t n, int shift, uint32_t
     table[(int64_t)tid * nblocks + b] = hist[tid];
 }
 
-__global__ void __launch_bounds__(kSortWarps * 32)
+static __global__ void __launch_bounds__(kSortWarps * 32)
 sort_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int64_t n, int shift, uint32_t mask,
                     const uint32_t *__restrict__ table, int64_t nblocks)
 {
@@ -167,6 +257,8 @@ inline cudaError_t radix_sort_u64(uint64_t *a, uint64_t *b, int64_t n, int bit_l
     int passes = (n_bits + 7) / 8;
     int per = (n_bits + passes - 1) / passes;
     uint32_t *table = (uint32_t *)ws;
+    size_t toff = ((sort_table_entries(n) + 64) * sizeof(uint32_t) + 255) / 256 * 256;
+    uint32_t *scan_tmp = (uint32_t *)((char *)ws + toff);
     int64_t nb = sort_num_blocks(n);
     uint64_t *src = a, *dst = b;
     int done = 0;
@@ -175,9 +267,10 @@ inline cudaError_t radix_sort_u64(uint64_t *a, uint64_t *b, int64_t n, int bit_l
         uint32_t mask = (1u << bits) - 1u;
         int shift = bit_lo + done;
         sort_hist_kernel<<<(unsigned)nb, kSortWarps * 32, 0, s>>>(src, n, shift, mask, table, nb);
-        scan_exclusive_kernel<uint32_t><<<1, kScanThreads, 0, s>>>(table, nb * kRadix, nullptr);
+        cudaError_t e = scan_exclusive<uint32_t>(table, nb * kRadix, scan_tmp, nullptr, s, launches);
+        if (e != cudaSuccess) return e;
         sort_scatter_kernel<<<(unsigned)nb, kSortWarps * 32, 0, s>>>(src, dst, n, shift, mask, table, nb);
-        if (launches) *launches += 3;
+        if (launches) *launches += 2;
         uint64_t *t = src; src = dst; dst = t;
         done += bits;
     }

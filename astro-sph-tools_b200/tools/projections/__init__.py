@@ -3,3 +3,4 @@ from ._projector import create_image, create_images, default_projector
 from ._kernels import (quartic_spline_kernel, wendland_c2_kernel, wendland_c2_kernel_3d, cubic_spline_kernel_2d,
                        kernel_id_of)
 from ._engine import Projector2D
+from ._gridder import create_grid, Gridder3D, default_gridder

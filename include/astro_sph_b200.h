@@ -142,6 +142,13 @@ int ast_grid3d_workspace_bytes(const ast_grid3d_params *p, size_t *bytes);
 int ast_grid3d(const ast_grid3d_params *p, const double *pos, const double *h, const double *prop,
                double *out, void *workspace, size_t workspace_bytes, void *stream, ast_project2d_stats *stats);
 
+/* 3-D index work for the bit-exact parity tests: bbox n_img*N*6 int32 (x0,x1,y0,y1,z0,z1), cls n_img*N uint8,
+ * pairs_sorted pair_capacity uint64 = (sort_key << 32) | particle with sort_key = brick_key * (periodic ? 32 : 1) + image,
+ * brick_key = (bx*nby + by)*nbz + bz; huge = (image << 32) | particle; counts (host) = {pairs, huge}.  Synchronises. */
+int ast_bin3d(const ast_grid3d_params *p, const double *pos, const double *h, int32_t *bbox, uint8_t *cls,
+              uint64_t *pairs_sorted, uint64_t *huge, int64_t *counts, void *workspace, size_t workspace_bytes,
+              void *stream);
+
 /* ---- smoothing lengths by k nearest neighbours, replaces the KDTree branch of
  * SnapshotSWIFT.get_smoothing_lengths (io/SWIFT/_SnapshotSWIFT.py:62-83):
  *   h_out[i] = K-th smallest sqrt((dx*dx+dy*dy)+dz*dz) over all particles j, i itself included;
@@ -155,7 +162,10 @@ typedef struct ast_knn_params {
     int32_t flags;
     double box;                  /* > 0: periodic cube [0, box)^3 ; <= 0: open */
     double lo[3], hi[3];         /* extent of the positions (open box); ignored when periodic */
-    double cell_target;          /* mean particles per cell; <= 0 = default */
+    double cell_target;          /* mean particles per cell; <= 0 = default (k/3) */
+    int64_t q_begin, q_count;    /* queries = particles [q_begin, q_begin + q_count); q_count <= 0 = all.  Multi-GPU:
+                                    every rank holds all positions and answers its own slice of the queries.
+                                    h_out / idx_out / dist_out hold q_count rows, row = particle - q_begin. */
 } ast_knn_params;
 
 int ast_knn_workspace_bytes(const ast_knn_params *p, size_t *bytes);

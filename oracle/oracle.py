@@ -35,6 +35,7 @@ def lib():
         _LIB.orc_kernel_eval.restype = C.c_double
         _LIB.orc_kernel_eval.argtypes = [C.c_int, C.c_double, C.c_double]
         _LIB.orc_bin2d.restype = C.c_int64
+        _LIB.orc_bin3d.restype = C.c_int64
         _LIB.orc_max_threads.restype = C.c_int
     return _LIB
 
@@ -173,6 +174,28 @@ def bbox3d(pos, h, grid_size, lo, hi, periodic=False, box=None):
     lib().orc_bbox3d(_p(pos), _p(h), C.c_int64(N), C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(lo), _p(hi), C.c_int(n_img),
                      _p(np.ascontiguousarray(s3)), _p(out))
     return out
+
+
+def bin3d(pos, h, grid_size, lo, hi, brick=8, small_max_vox=64, huge_min_bricks=512, periodic=False, box=None, brute=False):
+    """3-D index work: dict(cls, pairs (emit order), sorted (stable by key), huge)."""
+    pos, h, N = _common(pos, h)
+    nx, ny, nz = (int(v) for v in grid_size)
+    lo = _f64(lo); hi = _f64(hi)
+    n_img, s3 = images3(periodic, box)
+    s3 = np.ascontiguousarray(s3)
+    args = [_p(pos), _p(h), C.c_int64(N), C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(lo), _p(hi), C.c_int(n_img), _p(s3),
+            C.c_int(brick), C.c_int64(small_max_vox), C.c_int64(huge_min_bricks), C.c_int(int(brute))]
+    nh = C.c_int64(0)
+    cls = np.zeros(n_img * N, dtype=np.uint8)
+    npairs = lib().orc_bin3d(*args, _p(cls), None, None, C.byref(nh))
+    pairs = np.empty(max(npairs, 1), dtype=np.uint64)
+    huge = np.empty(max(nh.value, 1), dtype=np.uint64)
+    lib().orc_bin3d(*args, _p(cls), _p(pairs), _p(huge), C.byref(nh))
+    pairs = pairs[:npairs]; huge = huge[:nh.value]
+    s = pairs.copy(); tmp = np.empty_like(s)
+    if npairs:
+        lib().orc_sort_pairs_stable(_p(s), C.c_int64(npairs), _p(tmp))
+    return dict(cls=cls.reshape(n_img, N), pairs=pairs, sorted=s, huge=huge)
 
 
 def knn_brute(pos, k, box=0.0, want_lists=False):

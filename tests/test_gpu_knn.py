@@ -1,0 +1,85 @@
+"""-m gpu: smoothing-length k-NN (ast_knn_h through the Python host layer) against scipy.spatial.cKDTree, the
+reference's actual arithmetic.  Distances must be BIT-EQUAL; neighbour indices equal wherever distances are distinct
+(inside groups of exactly equal distance scipy's order is traversal dependent)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_knn(pos, k, box=None, lists=False, **kw):
+    import torch
+    from astro_sph_tools_b200.tools.smoothing import SmoothingLengthSolver
+    sol = SmoothingLengthSolver(cell_target=kw.pop("cell_target", 0.0))
+    pos_d = torch.from_numpy(np.ascontiguousarray(pos)).cuda()
+    res = sol.solve(pos_d, k, box, want_neighbours=lists, want_distances=lists, **kw)
+    torch.cuda.synchronize()
+    if lists:
+        return tuple(t.cpu().numpy() for t in res)
+    return res.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,k,box", [(20000, 32, None), (30000, 48, 1.0), (5000, 1, None), (4097, 64, 1.0), (3000, 100, None)])
+def test_h_bit_equal_to_scipy(oracle, n, k, box):
+    rng = np.random.default_rng(n + k)
+    pos = rng.uniform(0, 1.0, (n, 3))
+    h_ref = oracle.knn_scipy(pos, k, box, workers=-1)[0]
+    h = gpu_knn(pos, k, box)
+    assert np.array_equal(h, h_ref)
+
+
+def test_reference_default_api(oracle):
+    """get_smoothing_lengths(positions): K = 32, self included, non-periodic == the reference's KDTree branch"""
+    from astro_sph_tools_b200.tools.smoothing import get_smoothing_lengths, compute_smoothing_lengths
+    pos = np.random.default_rng(0).normal(size=(8000, 3)) * [1.0, 3.0, 0.2] + 50.0      # anisotropic, offset extent
+    h = get_smoothing_lengths(pos)
+    assert np.array_equal(h, oracle.knn_scipy(pos, 32)[0])
+    h48 = compute_smoothing_lengths(np.mod(pos, 7.0), k=48, box_size=7.0)
+    assert np.array_equal(h48, oracle.knn_scipy(np.mod(pos, 7.0), 48, 7.0)[0])
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        get_smoothing_lengths(pos.astype(np.float32))
+
+
+def test_clustered_and_lattice_sets(oracle):
+    from astro_sph_tools_b200 import synthetic
+    pos, _ = synthetic.s2_positions(40000, 1.0, n_haloes=8, seed=3)
+    assert np.array_equal(gpu_knn(pos, 48, 1.0), oracle.knn_scipy(pos, 48, 1.0, workers=-1)[0])
+    s = synthetic.s1(24, k=48)                       # S1 recipe: h from scipy inside the generator
+    assert np.array_equal(gpu_knn(s["pos"], 48, 1.0), s["h"])
+
+
+def test_neighbour_lists_and_ties(oracle):
+    rng = np.random.default_rng(9)
+    pos = rng.uniform(0, 1, (6000, 3))
+    h, idx, dist = gpu_knn(pos, 16, None, lists=True)
+    h_ref, d_ref, i_ref = oracle.knn_scipy(pos, 16)
+    assert np.array_equal(dist, d_ref) and np.array_equal(h, h_ref)
+    assert np.array_equal(idx, i_ref.astype(np.int32))
+    # exact duplicates: distances still bit-equal, index SETS equal per group of equal distance
+    pos2 = np.concatenate([pos[:2000], pos[:2000], pos[:2000]])
+    h, idx, dist = gpu_knn(pos2, 8, None, lists=True)
+    h_ref, d_ref, i_ref = oracle.knn_scipy(pos2, 8)
+    assert np.array_equal(dist, d_ref)
+    for r in range(0, 6000, 97):
+        for d in np.unique(d_ref[r, :-1][d_ref[r, :-1] < d_ref[r, -1]]):          # complete tie groups only
+            assert set(idx[r][dist[r] == d]) == set(i_ref[r][d_ref[r] == d])
+
+
+def test_edge_cases(oracle):
+    pos = np.random.default_rng(1).uniform(0, 1, (10, 3))
+    assert np.all(np.isinf(gpu_knn(pos, 32)))                       # fewer points than k: inf, like scipy
+    one = gpu_knn(pos[:1], 1)
+    assert one.shape == (1,) and one[0] == 0.0
+    flat = pos.copy(); flat[:, 2] = 0.25                            # degenerate extent along z
+    assert np.array_equal(gpu_knn(flat, 4), oracle.knn_scipy(flat, 4)[0])
+
+
+def test_query_slices_and_cell_size_invariance(oracle):
+    rng = np.random.default_rng(12)
+    pos = rng.uniform(0, 1, (25000, 3))
+    full = gpu_knn(pos, 48, 1.0)
+    # multi-GPU decomposition: every rank answers a slice of the queries against all positions
+    parts = [gpu_knn(pos, 48, 1.0, q_begin=lo, q_count=hi - lo) for lo, hi in ((0, 6250), (6250, 12500), (12500, 25000))]
+    assert np.array_equal(np.concatenate(parts), full)
+    for ct in (2.0, 7.0, 40.0, 500.0):
+        assert np.array_equal(gpu_knn(pos, 48, 1.0, cell_target=ct), full)
