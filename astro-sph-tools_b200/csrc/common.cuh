@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/astro_sph_b200.h"
 
@@ -26,6 +27,23 @@ void set_error(const char *fmt, ...);          // defined in capi_common.cu (thr
             ast::set_error(__VA_ARGS__); \
             return AST_EINVAL;          \
         }                               \
+    } while (0)
+
+// AST_DEBUG_SYNC=1 in the environment: synchronise after every kernel and name the one that faulted
+inline bool debug_sync_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("AST_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+#define AST_KERNEL_CHECK(stream, name)                                                              \
+    do {                                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e == cudaSuccess && ast::debug_sync_enabled()) _e = cudaStreamSynchronize(stream);     \
+        if (_e != cudaSuccess) {                                                                    \
+            ast::set_error("%s:%d: kernel %s failed: %s", __FILE__, __LINE__, name, cudaGetErrorString(_e)); \
+            return AST_ECUDA;                                                                       \
+        }                                                                                           \
     } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -18,7 +18,6 @@ namespace ast {
 
 constexpr int BRICK = AST_BRICK;
 constexpr int kBin3Threads = 256;
-constexpr int kMaxImg3 = 27;
 constexpr int kAcc3Threads = 128;
 constexpr int kChunk3 = 128;
 
@@ -36,9 +35,19 @@ struct P3 {
     Axis1 ax[3];
     int nb[3];                       // bricks per axis
     int n_img, img_shift;
-    double shift[kMaxImg3][3];
+    double box[3];                   // periodic image m = 9*(ia+1) + 3*(ib+1) + (ic+1), shift = (ia,ib,ic) * box
     int64_t small_max_vox, huge_min_bricks;
 };
+
+
+// periodic image shift along axis c of image m (0 when there is a single image).  Computed arithmetically: a table in
+// kernel-parameter space indexed by the loop counter made ptxas keep the counter in a uniform register across the
+// divergent early returns of classify3 and the kernel faulted on some inputs.
+__host__ __device__ __forceinline__ double image_shift3(int n_img, const double *box, int m, int c)
+{
+    const int t = c == 0 ? m / 9 : (c == 1 ? (m / 3) % 3 : m % 3);
+    return n_img == 1 ? 0.0 : (double)(t - 1) * box[c];
+}
 
 template <int SHAPE>
 __device__ __forceinline__ void deposit_small3(const P3 &p, const Bin3 &b, const double *q, double h, double R2, double coef)
@@ -70,7 +79,7 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
         const double h = p.h[i], R2 = radius2(h);
         bool need_rec = false;
         for (int m = 0; m < p.n_img; ++m) {
-            const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+            const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
             Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
             if (b.cls == CLS_SMALL) {
                 if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * kernel_norm(p.kernel_id, h));
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_
         h = p.h[i];
         R2 = radius2(h);
         for (int m = 0; m < p.n_img; ++m) {
-            const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+            const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
             Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
             if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
             else if (b.cls == CLS_HUGE) ++nhuge;
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_
     uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
     if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
     for (int m = 0; m < p.n_img; ++m) {
-        const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+        const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
         Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
         if (b.cls == CLS_TILED) {
             for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [&](uint32_t key) {
@@ -161,8 +170,8 @@ struct Acc3 {
     const Rec3 *rec;
     double *out;
     double lo[3], d[3], inv_d[3];
-    int n[3], nb[3], img_shift;
-    double shift[kMaxImg3][3];
+    int n[3], nb[3], img_shift, n_img;
+    double box[3];
 };
 
 template <int SHAPE>
@@ -204,9 +213,9 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
                 m = (uint32_t)(e >> 32);
             }
             const Rec3 r = a.rec[idx];
-            const float fx = (float)((r.x + a.shift[m][0] - a.lo[0]) * a.inv_d[0] - (double)X0);
-            const float fy = (float)((r.y + a.shift[m][1] - a.lo[1]) * a.inv_d[1] - (double)Y0);
-            const float fz = (float)((r.z + a.shift[m][2] - a.lo[2]) * a.inv_d[2] - (double)Z0);
+            const float fx = (float)((r.x + image_shift3(a.n_img, a.box, (int)m, 0) - a.lo[0]) * a.inv_d[0] - (double)X0);
+            const float fy = (float)((r.y + image_shift3(a.n_img, a.box, (int)m, 1) - a.lo[1]) * a.inv_d[1] - (double)Y0);
+            const float fz = (float)((r.z + image_shift3(a.n_img, a.box, (int)m, 2) - a.lo[2]) * a.inv_d[2] - (double)Z0);
             const double inv_h = 1.0 / (double)r.h;
             const float sx = (float)(a.d[0] * inv_h), sy = (float)(a.d[1] * inv_h), sz = (float)(a.d[2] * inv_h);
             P = make_float4(fx * sx, fy * sy, fz * sz, r.c);
@@ -268,7 +277,7 @@ __global__ void bbox_cls3_kernel(P3 p, int32_t *__restrict__ bbox, uint8_t *__re
     const double x0[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
     const double h = p.h[i], R2 = radius2(h);
     for (int m = 0; m < p.n_img; ++m) {
-        const double q[3] = { AST_DADD(x0[0], p.shift[m][0]), AST_DADD(x0[1], p.shift[m][1]), AST_DADD(x0[2], p.shift[m][2]) };
+        const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
         Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
         const int64_t j = (int64_t)m * p.n + i;
         if (bbox)
@@ -343,11 +352,7 @@ static P3 make_p3(const ast_grid3d_params *p, const double *pos, const double *h
     const bool per = (p->flags & AST_FLAG_PERIODIC) != 0;
     a.n_img = per ? 27 : 1;
     a.img_shift = per ? 5 : 0;
-    for (int m = 0; m < kMaxImg3; ++m) {            // image m = 9*(ia+1) + 3*(ib+1) + (ic+1)
-        a.shift[m][0] = per ? (double)(m / 9 - 1) * p->box[0] : 0.0;
-        a.shift[m][1] = per ? (double)((m / 3) % 3 - 1) * p->box[1] : 0.0;
-        a.shift[m][2] = per ? (double)(m % 3 - 1) * p->box[2] : 0.0;
-    }
+    for (int c = 0; c < 3; ++c) a.box[c] = per ? p->box[c] : 0.0;
     a.small_max_vox = p->small_max_vox >= 0 ? p->small_max_vox : kDefaultSmallMaxVox;
     a.huge_min_bricks = p->huge_min_bricks >= 0 ? p->huge_min_bricks : kDefaultHugeMinBricks;
     return a;
@@ -425,7 +430,8 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
             c.lo[k] = a.ax[k].vmin; c.d[k] = a.ax[k].d; c.inv_d[k] = a.ax[k].inv_d; c.n[k] = a.ax[k].n; c.nb[k] = a.nb[k];
         }
         c.img_shift = a.img_shift;
-        memcpy(c.shift, a.shift, sizeof c.shift);
+        c.n_img = a.n_img;
+        for (int k = 0; k < 3; ++k) c.box[k] = a.box[k];
         for (int64_t r = 0; r < rounds; ++r) {
             const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
             const int64_t nw = (int64_t)(w1 - w0);
@@ -483,10 +489,12 @@ extern "C" int ast_bin3d(const ast_grid3d_params *p, const double *pos, const do
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
     if (p->n > 0) {
         if (bbox || cls) bbox_cls3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, bbox, cls);
+        AST_KERNEL_CHECK(s, "bbox_cls3_kernel");
         bin3_kernel<SHAPE_CUBIC, false><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        AST_KERNEL_CHECK(s, "bin3_kernel");
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
-        AST_CUDA_TRY(cudaGetLastError());
+        AST_KERNEL_CHECK(s, "scan_exclusive_kernel");
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaStreamSynchronize(s));

@@ -30,7 +30,6 @@ namespace ast {
 
 constexpr int TILE = AST_TILE;
 constexpr int kBinThreads = 256;
-constexpr int kMaxImg = 9;
 constexpr int kAccThreads = 128;
 constexpr int kChunk = 128;            // list entries staged per pass
 
@@ -48,10 +47,15 @@ struct P2 {
     int a_col, b_col, n_prop, kernel_id, shape;
     Axis1 ax, ay;
     int ntx, nty, n_img, img_shift;     // sort key = tile_key << img_shift | image
-    double shift_a[kMaxImg], shift_b[kMaxImg];
+    double box_a, box_b;                // periodic image m = 3*(ia+1) + (ib+1), shift = (ia*box_a, ib*box_b)
     int64_t small_max_px, huge_min_tiles;
     size_t map_stride;
 };
+
+
+// periodic image shifts (0 for a single image); arithmetic instead of a parameter-space table, see grid3d.cu
+__host__ __device__ __forceinline__ double image_shift_a(int n_img, double box_a, int m) { return n_img == 1 ? 0.0 : (double)(m / 3 - 1) * box_a; }
+__host__ __device__ __forceinline__ double image_shift_b(int n_img, double box_b, int m) { return n_img == 1 ? 0.0 : (double)(m % 3 - 1) * box_b; }
 
 // direct deposit of a small-footprint particle image: exact float64 mask, float32 shape, float64 atomics
 template <int SHAPE>
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict_
         double coef[AST_MAX_PROPS];
         bool have_coef = false;
         for (int m = 0; m < p.n_img; ++m) {
-            const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+            const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
             Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
             if (b.cls == CLS_SMALL) {
                 if (DEPOSIT) {
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
         pa0 = p.pos[3 * i + p.a_col]; pb0 = p.pos[3 * i + p.b_col]; h = p.h[i];
         R2 = radius2(h);
         for (int m = 0; m < p.n_img; ++m) {
-            const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+            const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
             Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
             if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
             else if (b.cls == CLS_HUGE) ++nhuge;
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
     uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
     if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
     for (int m = 0; m < p.n_img; ++m) {
-        const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+        const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
         Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
         if (b.cls == CLS_TILED) {
             for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [&](uint32_t key) {
@@ -188,8 +192,8 @@ struct Acc {
     const Rec *rec;
     double *out;
     double x_min, y_min, dx, dy, inv_dx, inv_dy;
-    int nx, ny, ntx, nty, img_shift;
-    double shift_a[kMaxImg], shift_b[kMaxImg];
+    int nx, ny, ntx, nty, img_shift, n_img;
+    double box_a, box_b;
     size_t map_stride;
 };
 
@@ -240,8 +244,8 @@ __global__ void __launch_bounds__(kAccThreads) tile_accum_kernel(Acc a)
                 m = (uint32_t)(e >> 32);
             }
             const Rec r = a.rec[idx];
-            const double ux = (r.pa + a.shift_a[m] - a.x_min) * a.inv_dx - ox;
-            const double uy = (r.pb + a.shift_b[m] - a.y_min) * a.inv_dy - oy;
+            const double ux = (r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox;
+            const double uy = (r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy;
             const float sx = (float)(a.dx / r.h), sy = (float)(a.dy / r.h);
             const float fx = (float)ux, fy = (float)uy;
             P = make_float4(fx * sx, fy * sy, sx, sy);
@@ -326,7 +330,7 @@ __global__ void contrib_count_kernel(P2 p, int32_t *__restrict__ count)
     const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i];
     const double R2 = radius2(h);
     for (int m = 0; m < p.n_img; ++m) {
-        const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+        const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
         int x0, x1, y0, y1;
         if (!range1(p.ax, pa, h, R2, x0, x1) || !range1(p.ay, pb, h, R2, y0, y1)) continue;
         for (int xi = x0; xi <= x1; ++xi) {
@@ -345,7 +349,7 @@ __global__ void bbox_cls_kernel(P2 p, int32_t *__restrict__ bbox, uint8_t *__res
     const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i];
     const double R2 = radius2(h);
     for (int m = 0; m < p.n_img; ++m) {
-        const double pa = AST_DADD(pa0, p.shift_a[m]), pb = AST_DADD(pb0, p.shift_b[m]);
+        const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
         Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
         const int64_t j = (int64_t)m * p.n + i;
         if (bbox) {
@@ -433,10 +437,8 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     const bool per = (p->flags & AST_FLAG_PERIODIC) != 0;
     a.n_img = per ? 9 : 1;
     a.img_shift = per ? 4 : 0;
-    for (int m = 0; m < kMaxImg; ++m) {
-        a.shift_a[m] = per ? (double)(m / 3 - 1) * p->box_a : 0.0;   // image m = 3*(ia+1) + (ib+1)
-        a.shift_b[m] = per ? (double)(m % 3 - 1) * p->box_b : 0.0;
-    }
+    a.box_a = per ? p->box_a : 0.0;
+    a.box_b = per ? p->box_b : 0.0;
     a.small_max_px = p->small_max_px >= 0 ? p->small_max_px : kDefaultSmallMaxPx;
     a.huge_min_tiles = p->huge_min_tiles >= 0 ? p->huge_min_tiles : kDefaultHugeMinTiles;
     a.map_stride = (size_t)p->nx * (size_t)p->ny;
@@ -525,7 +527,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
         c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
         c.x_min = a.ax.vmin; c.y_min = a.ay.vmin; c.dx = a.ax.d; c.dy = a.ay.d; c.inv_dx = a.ax.inv_d; c.inv_dy = a.ay.inv_d;
         c.nx = p->nx; c.ny = p->ny; c.ntx = a.ntx; c.nty = a.nty; c.img_shift = a.img_shift;
-        for (int m = 0; m < kMaxImg; ++m) { c.shift_a[m] = a.shift_a[m]; c.shift_b[m] = a.shift_b[m]; }
+        c.n_img = a.n_img; c.box_a = a.box_a; c.box_b = a.box_b;
         c.map_stride = a.map_stride;
         for (int64_t r = 0; r < rounds; ++r) {
             const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
