@@ -1,0 +1,71 @@
+"""Host-side multi-GPU logic on the CPU: world_size-2 gloo.  Particles shard by index, every rank produces a
+partial map (here: the CPU oracle stands in for the per-rank CUDA deposit, which needs a GPU), the partial maps are
+summed with the same `reduce_maps` collective bench.py and create_images_sharded use (NCCL on GPUs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, random_cloud, rel_l2
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, all_ranks, q):
+    import sys
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from astro_sph_tools_b200 import distributed as astd
+    pos, h, prop = random_cloud(21, 3001, h_hi=0.8, signed=True)
+    lo, hi = astd.shard_bounds(len(h), world, rank)
+    part = oracle.project2d(pos[lo:hi], h[lo:hi], prop[lo:hi], (64, 64), 2, 0.0, 10.0, 0.0, 10.0)
+    t = astd.reduce_maps(torch.from_numpy(part.copy()), dst=0, all_ranks=all_ranks)
+    if rank == 0 or all_ranks:
+        full = oracle.project2d(pos, h, prop, (64, 64), 2, 0.0, 10.0, 0.0, 10.0)
+        q.put((rank, rel_l2(t.numpy(), full), lo, hi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("all_ranks", [False, True])
+def test_sharded_maps_sum_to_full_map(all_ranks):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, all_ranks, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = []
+    while not q.empty():
+        got.append(q.get())
+    assert len(got) == (2 if all_ranks else 1)
+    for rank, err, lo, hi in got:
+        assert err < 1e-13
+
+
+def test_shard_bounds_cover_everything_once():
+    from astro_sph_tools_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def test_reduce_is_identity_without_process_group():
+    from astro_sph_tools_b200.distributed import reduce_maps
+    t = torch.arange(6, dtype=torch.float64)
+    assert reduce_maps(t) is t
