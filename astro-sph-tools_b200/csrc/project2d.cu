@@ -34,8 +34,10 @@ constexpr int kAccThreads = 128;
 constexpr int kChunk = 128;            // list entries staged per pass
 
 struct __align__(32) Rec {
-    double pa, pb, h;
-    float c[AST_MAX_PROPS];
+    double pa, pb;             // in-plane position, float64 (tile-relative float32 is derived at staging time)
+    float inv_h;               // 1/h, computed in float64 and narrowed once per particle
+    float c[AST_MAX_PROPS];    // prop * norm(h)
+    float pad;
 };
 static_assert(sizeof(Rec) == 32, "record is one 32-byte sector");
 
@@ -77,6 +79,44 @@ __device__ __forceinline__ void deposit_small(const P2 &p, const Box2 &bb, doubl
     }
 }
 
+// Sub-pixel fast path of the direct deposit: when the support diameter 4h is below two pixels on both axes
+// (2h*inv_d <= 1 - 1e-9) at most the two samples at/after the particle can satisfy the 1-D condition on each axis, so
+// the canonical bbox is at most 2x2 (class "direct" whenever small_max_px >= 4) and the four candidates are tested with
+// the exact float64 mask directly -- no bbox search.  This is the HBM-bound regime of the path.
+template <int SHAPE>
+__device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double pb, double h, double R2, int64_t i)
+{
+    const double tx = AST_DMUL(AST_DSUB(pa, p.ax.vmin), p.ax.inv_d), ty = AST_DMUL(AST_DSUB(pb, p.ay.vmin), p.ay.inv_d);
+    if (!(tx > -2.0 && tx < (double)p.ax.n + 1.0 && ty > -2.0 && ty < (double)p.ay.n + 1.0)) return;   // also NaN / inf
+    const int i0 = (int)floor(tx), j0 = (int)floor(ty);
+    double dx2[2], dy2[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        dx2[k] = (i0 + k >= 0 && i0 + k < p.ax.n) ? dist2(p.ax, pa, i0 + k) : INFINITY;
+        dy2[k] = (j0 + k >= 0 && j0 + k < p.ay.n) ? dist2(p.ay, pb, j0 + k) : INFINITY;
+    }
+    double coef[AST_MAX_PROPS];
+    bool have = false;
+    float inv_h2 = 0.f;
+#pragma unroll
+    for (int kx = 0; kx < 2; ++kx)
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky) {
+            const double r2 = AST_DADD(dx2[kx], dy2[ky]);
+            if (r2 < R2) {
+                if (!have) {
+                    const double nrm = kernel_norm(p.kernel_id, h);
+                    for (int k = 0; k < p.n_prop; ++k) coef[k] = p.prop[k][i] * nrm;
+                    inv_h2 = __frcp_rn((float)(h * h));
+                    have = true;
+                }
+                const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2));
+                double *o = p.out + (size_t)(i0 + kx) * (size_t)p.ay.n + (size_t)(j0 + ky);
+                for (int k = 0; k < p.n_prop; ++k) atomicAdd(o + k * p.map_stride, coef[k] * f);
+            }
+        }
+}
+
 // K1.  DEPOSIT=false is the index-only variant used by ast_bin2d.
 template <int SHAPE, bool DEPOSIT>
 __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
@@ -91,39 +131,48 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict_
         bool need_rec = false;
         double coef[AST_MAX_PROPS];
         bool have_coef = false;
-        for (int m = 0; m < p.n_img; ++m) {
-            const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
-            Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
-            if (b.cls == CLS_SMALL) {
-                if (DEPOSIT) {
-                    if (!have_coef) {
-                        const double nrm = kernel_norm(p.kernel_id, h);
-                        for (int k = 0; k < p.n_prop; ++k) coef[k] = p.prop[k][i] * nrm;
-                        have_coef = true;
+        const double h2 = AST_DMUL(2.0, h);
+        const bool subpixel = p.small_max_px >= 4 && h > 0.0 && h2 * p.ax.inv_d <= 1.0 - 1e-9 && h2 * p.ay.inv_d <= 1.0 - 1e-9;
+        if (subpixel) {
+            if (DEPOSIT)
+                for (int m = 0; m < p.n_img; ++m)
+                    deposit_subpixel<SHAPE>(p, AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)),
+                                            AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m)), h, R2, i);
+        } else {
+            for (int m = 0; m < p.n_img; ++m) {
+                const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
+                Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+                if (b.cls == CLS_SMALL) {
+                    if (DEPOSIT) {
+                        if (!have_coef) {
+                            const double nrm = kernel_norm(p.kernel_id, h);
+                            for (int k = 0; k < p.n_prop; ++k) coef[k] = p.prop[k][i] * nrm;
+                            have_coef = true;
+                        }
+                        deposit_small<SHAPE>(p, b.bb, pa, pb, h, R2, coef);
                     }
-                    deposit_small<SHAPE>(p, b.bb, pa, pb, h, R2, coef);
+                } else if (b.cls == CLS_TILED) {
+                    npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
+                    need_rec = true;
+                } else if (b.cls == CLS_HUGE) {
+                    ++nhuge;
+                    need_rec = true;
                 }
-            } else if (b.cls == CLS_TILED) {
-                npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
-                need_rec = true;
-            } else if (b.cls == CLS_HUGE) {
-                ++nhuge;
-                need_rec = true;
             }
         }
         if (need_rec && DEPOSIT) {
             const double nrm = kernel_norm(p.kernel_id, h);
             Rec r;
-            r.pa = pa0; r.pb = pb0; r.h = h;
+            r.pa = pa0; r.pb = pb0; r.inv_h = (float)(1.0 / h); r.pad = 0.f;
             for (int k = 0; k < AST_MAX_PROPS; ++k) r.c[k] = k < p.n_prop ? (float)(p.prop[k][i] * nrm) : 0.f;
             rec[i] = r;
         }
     }
-    uint32_t tp = block_sum_u32(npairs, red);
-    uint32_t th = block_sum_u32(nhuge, red);
+    // one reduction for both counts: per block pairs <= 256 * 9 * 256 < 2^20 and large-h entries <= 256 * 9 < 2^12
+    const uint32_t packed = block_sum_u32((nhuge << 20) | npairs, red);
     if (threadIdx.x == 0) {
-        block_pairs[blockIdx.x] = tp;
-        block_huge[blockIdx.x] = th;
+        block_pairs[blockIdx.x] = packed & 0xfffffu;
+        block_huge[blockIdx.x] = packed >> 20;
     }
 }
 
@@ -246,7 +295,7 @@ __global__ void __launch_bounds__(kAccThreads) tile_accum_kernel(Acc a)
             const Rec r = a.rec[idx];
             const double ux = (r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox;
             const double uy = (r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy;
-            const float sx = (float)(a.dx / r.h), sy = (float)(a.dy / r.h);
+            const float sx = (float)a.dx * r.inv_h, sy = (float)a.dy * r.inv_h;
             const float fx = (float)ux, fy = (float)uy;
             P = make_float4(fx * sx, fy * sy, sx, sy);
 #pragma unroll
@@ -317,6 +366,123 @@ __global__ void __launch_bounds__(kAccThreads) tile_accum_kernel(Acc a)
             for (int k = 0; k < NP; ++k) {
                 double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
                 *o += acc64[k][jx * 4 + jy];
+            }
+        }
+    }
+}
+
+
+// K6 (warp-autonomous variant): the CTA still maps to one 32x32 tile, but every warp walks the tile's list on its own for
+// its own sub-tile -- no CTA barrier anywhere.  Per 32 list entries: each lane stages one entry (float64 -> tile-relative
+// float32), tests it against the warp's sub-tile, the hits are compacted into the warp's private shared-memory slots with
+// a ballot, then all lanes evaluate the hits for their PX x PY pixel patch.  WX x WY warps tile the 32x32 pixels.
+template <int SHAPE, int NP, int WX, int WY, int PX, int PY>
+__global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
+{
+    constexpr int NW = WX * WY, SX = TILE / WX, SY = TILE / WY, LY = SY / PY, NPIX = PX * PY;
+    static_assert((SX / PX) * LY == 32, "a warp covers its sub-tile exactly");
+    __shared__ float4 sP[NW][32];       // {ux*sx, uy*sy, sx, sy}
+    __shared__ float2 sC[NW][32];       // {c0, c1}
+
+    const int tile = blockIdx.x;
+    const uint32_t beg = a.tbeg[tile], cnt = a.tend[tile] - beg;
+    const uint32_t total = cnt + a.n_huge;
+    if (total == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tile / a.nty, ty = tile - tx * a.nty;
+    const int X0 = tx * TILE, Y0 = ty * TILE;
+    const int sub_x = SX * (warp / WY), sub_y = SY * (warp % WY);          // sub-tile origin inside the tile
+    const int xl = sub_x + PX * (lane / LY), yl = sub_y + PY * (lane % LY);
+    float xf[PX], yf[PY];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) xf[i] = (float)(xl + i);
+#pragma unroll
+    for (int i = 0; i < PY; ++i) yf[i] = (float)(yl + i);
+    const float lox = (float)sub_x, hix = (float)(sub_x + SX - 1), loy = (float)sub_y, hiy = (float)(sub_y + SY - 1);
+    const float dxf = (float)a.dx, dyf = (float)a.dy;
+    const double ox = (double)X0, oy = (double)Y0;
+
+    float acc[NP][NPIX];
+    double acc64[NP][NPIX];
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+#pragma unroll
+        for (int j = 0; j < NPIX; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
+
+    int since_fold = 0;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        bool hit = false;
+        float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 C = make_float2(0.f, 0.f);
+        if (j < total) {
+            uint32_t idx, m;
+            if (j < cnt) {
+                const uint64_t e = a.sorted[beg + j];
+                idx = (uint32_t)e;
+                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
+            } else {
+                const uint64_t e = a.huge[j - cnt];
+                idx = (uint32_t)e;
+                m = (uint32_t)(e >> 32);
+            }
+            const Rec r = a.rec[idx];
+            const float fx = (float)((r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox);
+            const float fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
+            const float sx = dxf * r.inv_h, sy = dyf * r.inv_h;
+            const float ddx = fmaxf(fmaxf(lox - fx, fx - hix), 0.f) * sx;
+            const float ddy = fmaxf(fmaxf(loy - fy, fy - hiy), 0.f) * sy;
+            hit = ddx * ddx + ddy * ddy < 4.0001f;
+            P = make_float4(fx * sx, fy * sy, sx, sy);
+            C = make_float2(r.c[0], NP > 1 ? r.c[1] : 0.f);
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int dst = __popc(ball & ((1u << lane) - 1u));
+            sP[warp][dst] = P;
+            sC[warp][dst] = C;
+        }
+        __syncwarp();
+        const int nh = __popc(ball);
+        for (int e = 0; e < nh; ++e) {
+            const float4 q = sP[warp][e];
+            const float2 c = sC[warp][e];
+            float ax2[PX], by2[PY];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) { const float t = fmaf(-xf[i], q.z, q.x); ax2[i] = t * t; }
+#pragma unroll
+            for (int i = 0; i < PY; ++i) { const float t = fmaf(-yf[i], q.w, q.y); by2[i] = t * t; }
+#pragma unroll
+            for (int ix = 0; ix < PX; ++ix)
+#pragma unroll
+                for (int iy = 0; iy < PY; ++iy) {
+                    const float f = shape_eval<SHAPE>(fast_sqrt(ax2[ix] + by2[iy]));
+                    acc[0][ix * PY + iy] = fmaf(c.x, f, acc[0][ix * PY + iy]);
+                    if (NP > 1) acc[NP - 1][ix * PY + iy] = fmaf(c.y, f, acc[NP - 1][ix * PY + iy]);
+                }
+        }
+        __syncwarp();
+        since_fold += nh;
+        if (since_fold >= 96) {          // fold the float32 partial sums into float64 (warp-uniform condition)
+            since_fold = 0;
+#pragma unroll
+            for (int k = 0; k < NP; ++k)
+#pragma unroll
+                for (int jj = 0; jj < NPIX; ++jj) { acc64[k][jj] += (double)acc[k][jj]; acc[k][jj] = 0.f; }
+        }
+    }
+#pragma unroll
+    for (int ix = 0; ix < PX; ++ix) {
+        const int xi = X0 + xl + ix;
+        if (xi >= a.nx) continue;
+#pragma unroll
+        for (int iy = 0; iy < PY; ++iy) {
+            const int yi = Y0 + yl + iy;
+            if (yi >= a.ny) continue;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
+                *o += acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
             }
         }
     }
@@ -445,11 +611,30 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     return a;
 }
 
+// AST_ACCUM_VARIANT (tuning knob): 0 = CTA-cooperative staging, 1 = warp-autonomous 16x16 sub-tiles (4 warps, 2x4 pixels
+// per thread), 2 = warp-autonomous 8x16 sub-tiles (8 warps, 2x2 pixels per thread, default)
+static int accum_variant()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("AST_ACCUM_VARIANT"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; }
+    return v;
+}
+
+template <int SHAPE, int NP>
+static void launch_accum_np(const Acc &a, int64_t ntiles, cudaStream_t s)
+{
+    switch (accum_variant()) {
+    case 0: tile_accum_kernel<SHAPE, NP><<<(unsigned)ntiles, kAccThreads, 0, s>>>(a); break;
+    case 1: subtile_accum_kernel<SHAPE, NP, 2, 2, 2, 4><<<(unsigned)ntiles, 128, 0, s>>>(a); break;
+    default: subtile_accum_kernel<SHAPE, NP, 4, 2, 2, 2><<<(unsigned)ntiles, 256, 0, s>>>(a); break;
+    }
+}
+
 template <int SHAPE>
 static void launch_accum(int np, const Acc &a, int64_t ntiles, cudaStream_t s)
 {
-    if (np == 1) tile_accum_kernel<SHAPE, 1><<<(unsigned)ntiles, kAccThreads, 0, s>>>(a);
-    else tile_accum_kernel<SHAPE, 2><<<(unsigned)ntiles, kAccThreads, 0, s>>>(a);
+    if (np == 1) launch_accum_np<SHAPE, 1>(a, ntiles, s);
+    else launch_accum_np<SHAPE, 2>(a, ntiles, s);
 }
 
 }  // namespace ast
@@ -498,10 +683,9 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
         else bin_kernel<SHAPE_WENDLAND, true><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
         tk.end();
         tk.begin(1);
-        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
-        scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
+        scan2_exclusive_kernel<uint64_t><<<2, kScanThreads, 0, s>>>(L.block_pairs, L.block_huge, L.nb + 1);
         tk.end();
-        st.n_launches += 3;
+        st.n_launches += 2;
         AST_CUDA_TRY(cudaGetLastError());
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));

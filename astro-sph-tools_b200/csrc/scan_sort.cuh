@@ -68,6 +68,56 @@ __global__ void __launch_bounds__(kScanThreads) scan_exclusive_kernel(T *data, i
     if (tid == 0 && total_out) *total_out = carry_s;
 }
 
+// two independent arrays scanned by one launch (block 0 -> a, block 1 -> b)
+template <class T>
+__global__ void __launch_bounds__(kScanThreads) scan2_exclusive_kernel(T *a, T *b, int64_t n)
+{
+    T *data = blockIdx.x == 0 ? a : b;
+    __shared__ T warp_sum[32];
+    __shared__ T carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += (int64_t)kScanThreads * kScanItems) {
+        int64_t i0 = base + (int64_t)tid * kScanItems;
+        T v[kScanItems];
+        T s = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (i0 + k < n) ? data[i0 + k] : (T)0;
+            s += v[k];
+        }
+        T inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            T w = warp_sum[lane];
+            T winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                T t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sum[lane] = winc - w;
+        }
+        __syncthreads();
+        T excl = carry_s + warp_sum[warp] + (inc - s);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < n) data[i0 + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == kScanThreads - 1) carry_s = excl;
+        __syncthreads();
+    }
+}
+
 // ---- multi-block exclusive scan: per-block sums -> scan of the sums (single block) -> per-block scan + base.
 // One block handles kScanTile consecutive elements.
 constexpr int kScanTile = kScanThreads * kScanItems;      // 4096

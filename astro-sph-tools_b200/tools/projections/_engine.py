@@ -64,7 +64,7 @@ class Projector2D:
         p.huge_min_tiles = self.huge_min_tiles
         cap = self.pair_capacity
         if cap is None:
-            cap = min(max(8 * int(n), 1 << 20), 1 << 30)
+            cap = min(max(12 * int(n), 1 << 20), 1 << 30)
         p.pair_capacity = int(cap)
         p.huge_capacity = int(self.huge_capacity)
         return p

@@ -125,6 +125,27 @@ def test_edge_cases(oracle):
     check(m, ref)
 
 
+def test_subpixel_regime_exact_support(oracle):
+    """HBM-bound regime: supports below one pixel, particles on pixel corners; the direct-deposit path applies the exact
+    float64 mask, so the set of non-zero pixels must equal the oracle's contributor mask"""
+    from gpu_util import gpu_project
+    rng = np.random.default_rng(77)
+    n, npix = 50000, 200
+    d = 10.0 / npix
+    pos = rng.uniform(-0.2, 10.2, (n, 3))
+    on = rng.random(n) < 0.3
+    pos[on] = np.round(pos[on] / d) * d
+    h = rng.choice([0.05 * d, 0.2 * d, 0.25 * d, 0.4 * d, 0.4999 * d, 0.5 * d, 0.7 * d], n)
+    prop = rng.uniform(0.5, 1.5, n)
+    for periodic, box in ((False, None), (True, (10.0, 10.0))):
+        ref = oracle.project2d(pos, h, prop, (npix, npix), 2, 0.0, 10.0, 0.0, 10.0, periodic=periodic, box=box)
+        cnt = oracle.contrib_count2d(pos, h, (npix, npix), 2, 0.0, 10.0, 0.0, 10.0, periodic=periodic, box=box)
+        m, st = gpu_project(pos, h, prop, (npix, npix), 2, (0.0, 10.0, 0.0, 10.0), periodic=periodic, box=box)
+        assert st["n_pairs"] == 0
+        check(m, ref)
+        assert np.array_equal(m != 0, cnt > 0)
+
+
 def test_properties_linearity_permutation(oracle):
     from gpu_util import gpu_project
     pos, h, prop = random_cloud(14, 4000, h_hi=0.9, signed=True)
