@@ -46,7 +46,8 @@ struct P2 {
     const double *prop[AST_MAX_PROPS];
     double *out;
     int64_t n;
-    int a_col, b_col, n_prop, kernel_id, shape;
+    int a_col, b_col, n_prop, kernel_id, shape, norm_dim;
+    double norm_c;                      // norm(h) = norm_c / h^norm_dim
     Axis1 ax, ay;
     int ntx, nty, n_img, img_shift;     // sort key = tile_key << img_shift | image
     double box_a, box_b;                // periodic image m = 3*(ia+1) + (ib+1), shift = (ia*box_a, ib*box_b)
@@ -59,21 +60,35 @@ struct P2 {
 __host__ __device__ __forceinline__ double image_shift_a(int n_img, double box_a, int m) { return n_img == 1 ? 0.0 : (double)(m / 3 - 1) * box_a; }
 __host__ __device__ __forceinline__ double image_shift_b(int n_img, double box_b, int m) { return n_img == 1 ? 0.0 : (double)(m % 3 - 1) * box_b; }
 
+// 1/x to ~1e-15 relative: float32 reciprocal seed + one Newton step in float64 (an IEEE float64 division costs ~40
+// instructions on the device; weights only need 1e-7)
+__device__ __forceinline__ double fast_rcp64(double x)
+{
+    const double r = (double)__frcp_rn((float)x);
+    return r * (2.0 - x * r);
+}
+
+// norm(h) = norm_c * inv_h^2 (2-D normalisations) or norm_c * inv_h^3 (3-D), norm_c from kernel_norm(kid, 1)
+__device__ __forceinline__ double norm_from_inv_h(const P2 &p, double inv_h)
+{
+    const double t = p.norm_c * inv_h * inv_h;
+    return p.norm_dim == 3 ? t * inv_h : t;
+}
+
 // direct deposit of a small-footprint particle image: exact float64 mask, float32 shape, float64 atomics
-template <int SHAPE>
-__device__ __forceinline__ void deposit_small(const P2 &p, const Box2 &bb, double pa, double pb, double h, double R2,
+template <int SHAPE, int NP>
+__device__ __forceinline__ void deposit_small(const P2 &p, const Box2 &bb, double pa, double pb, double R2, float inv_h2,
                                               const double *coef)
 {
-    const double inv_h2 = 1.0 / (h * h);
     for (int xi = bb.x0; xi <= bb.x1; ++xi) {
         const double dx2 = dist2(p.ax, pa, xi);
         double *row = p.out + (size_t)xi * (size_t)p.ay.n;
         for (int yi = bb.y0; yi <= bb.y1; ++yi) {
             const double r2 = AST_DADD(dx2, dist2(p.ay, pb, yi));
             if (r2 < R2) {
-                const float q = fast_sqrt((float)(r2 * inv_h2));
-                const double f = (double)shape_eval<SHAPE>(q);
-                for (int k = 0; k < p.n_prop; ++k) atomicAdd(row + k * p.map_stride + yi, coef[k] * f);
+                const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2));
+#pragma unroll
+                for (int k = 0; k < NP; ++k) atomicAdd(row + k * p.map_stride + yi, coef[k] * f);
             }
         }
     }
@@ -83,8 +98,8 @@ __device__ __forceinline__ void deposit_small(const P2 &p, const Box2 &bb, doubl
 // (2h*inv_d <= 1 - 1e-9) at most the two samples at/after the particle can satisfy the 1-D condition on each axis, so
 // the canonical bbox is at most 2x2 (class "direct" whenever small_max_px >= 4) and the four candidates are tested with
 // the exact float64 mask directly -- no bbox search.  This is the HBM-bound regime of the path.
-template <int SHAPE>
-__device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double pb, double h, double R2, int64_t i)
+template <int SHAPE, int NP>
+__device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double pb, double R2, float inv_h2, const double *coef)
 {
     const double tx = AST_DMUL(AST_DSUB(pa, p.ax.vmin), p.ax.inv_d), ty = AST_DMUL(AST_DSUB(pb, p.ay.vmin), p.ay.inv_d);
     if (!(tx > -2.0 && tx < (double)p.ax.n + 1.0 && ty > -2.0 && ty < (double)p.ay.n + 1.0)) return;   // also NaN / inf
@@ -95,84 +110,180 @@ __device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double 
         dx2[k] = (i0 + k >= 0 && i0 + k < p.ax.n) ? dist2(p.ax, pa, i0 + k) : INFINITY;
         dy2[k] = (j0 + k >= 0 && j0 + k < p.ay.n) ? dist2(p.ay, pb, j0 + k) : INFINITY;
     }
-    double coef[AST_MAX_PROPS];
-    bool have = false;
-    float inv_h2 = 0.f;
 #pragma unroll
     for (int kx = 0; kx < 2; ++kx)
 #pragma unroll
         for (int ky = 0; ky < 2; ++ky) {
             const double r2 = AST_DADD(dx2[kx], dy2[ky]);
             if (r2 < R2) {
-                if (!have) {
-                    const double nrm = kernel_norm(p.kernel_id, h);
-                    for (int k = 0; k < p.n_prop; ++k) coef[k] = p.prop[k][i] * nrm;
-                    inv_h2 = __frcp_rn((float)(h * h));
-                    have = true;
-                }
                 const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2));
                 double *o = p.out + (size_t)(i0 + kx) * (size_t)p.ay.n + (size_t)(j0 + ky);
-                for (int k = 0; k < p.n_prop; ++k) atomicAdd(o + k * p.map_stride, coef[k] * f);
+#pragma unroll
+                for (int k = 0; k < NP; ++k) atomicAdd(o + k * p.map_stride, coef[k] * f);
             }
         }
 }
 
-// K1.  DEPOSIT=false is the index-only variant used by ast_bin2d.
-template <int SHAPE, bool DEPOSIT>
+// per-particle body of K1: classification, pair / large-h counts, direct deposit, record
+template <int SHAPE, bool DEPOSIT, int NP>
+__device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0, double pb0, double h, double *coef /* [NP] props */,
+                                             Rec *__restrict__ rec, uint32_t &npairs, uint32_t &nhuge)
+{
+    const double R2 = radius2(h);
+    const double h2 = AST_DMUL(2.0, h);
+    if (!(h > 0.0 && h2 < INFINITY)) return;
+    float inv_h2 = 0.f, inv_hf = 0.f;
+    if (DEPOSIT) {
+        const double inv_h = fast_rcp64(h);
+        const double nrm = norm_from_inv_h(p, inv_h);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) coef[k] *= nrm;
+        inv_hf = (float)inv_h;
+        inv_h2 = (float)(inv_h * inv_h);
+    }
+    const bool subpixel = p.small_max_px >= 4 && h2 * p.ax.inv_d <= 1.0 - 1e-9 && h2 * p.ay.inv_d <= 1.0 - 1e-9;
+    if (subpixel) {
+        if (DEPOSIT)
+            for (int m = 0; m < p.n_img; ++m)
+                deposit_subpixel<SHAPE, NP>(p, AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)),
+                                            AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m)), R2, inv_h2, coef);
+        return;
+    }
+    bool need_rec = false;
+    for (int m = 0; m < p.n_img; ++m) {
+        const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
+        Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+        if (b.cls == CLS_SMALL) {
+            if (DEPOSIT) deposit_small<SHAPE, NP>(p, b.bb, pa, pb, R2, inv_h2, coef);
+        } else if (b.cls == CLS_TILED) {
+            npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
+            need_rec = true;
+        } else if (b.cls == CLS_HUGE) {
+            ++nhuge;
+            need_rec = true;
+        }
+    }
+    if (need_rec && DEPOSIT) {
+        Rec r;
+        r.pa = pa0; r.pb = pb0; r.inv_h = inv_hf; r.pad = 0.f;
+#pragma unroll
+        for (int k = 0; k < AST_MAX_PROPS; ++k) r.c[k] = k < NP ? (float)coef[k < NP ? k : 0] : 0.f;
+        rec[i] = r;
+    }
+}
+
+// K1.  DEPOSIT=false is the index-only variant used by ast_bin2d (NP is then irrelevant).  One particle per thread,
+// plain global loads; block b of the launch handles particle block b + block_offset.
+template <int SHAPE, bool DEPOSIT, int NP>
 __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
-                                                          uint64_t *__restrict__ block_huge)
+                                                          uint64_t *__restrict__ block_huge, int64_t block_offset)
 {
     __shared__ uint32_t red[34];
-    const int64_t i = (int64_t)blockIdx.x * kBinThreads + threadIdx.x;
+    const int64_t blk = (int64_t)blockIdx.x + block_offset;
+    const int64_t i = blk * kBinThreads + threadIdx.x;
     uint32_t npairs = 0, nhuge = 0;
     if (i < p.n) {
+        // every load of this particle is issued before anything depends on one of them
         const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i];
-        const double R2 = radius2(h);
-        bool need_rec = false;
-        double coef[AST_MAX_PROPS];
-        bool have_coef = false;
-        const double h2 = AST_DMUL(2.0, h);
-        const bool subpixel = p.small_max_px >= 4 && h > 0.0 && h2 * p.ax.inv_d <= 1.0 - 1e-9 && h2 * p.ay.inv_d <= 1.0 - 1e-9;
-        if (subpixel) {
-            if (DEPOSIT)
-                for (int m = 0; m < p.n_img; ++m)
-                    deposit_subpixel<SHAPE>(p, AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)),
-                                            AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m)), h, R2, i);
-        } else {
-            for (int m = 0; m < p.n_img; ++m) {
-                const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
-                Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
-                if (b.cls == CLS_SMALL) {
-                    if (DEPOSIT) {
-                        if (!have_coef) {
-                            const double nrm = kernel_norm(p.kernel_id, h);
-                            for (int k = 0; k < p.n_prop; ++k) coef[k] = p.prop[k][i] * nrm;
-                            have_coef = true;
-                        }
-                        deposit_small<SHAPE>(p, b.bb, pa, pb, h, R2, coef);
-                    }
-                } else if (b.cls == CLS_TILED) {
-                    npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
-                    need_rec = true;
-                } else if (b.cls == CLS_HUGE) {
-                    ++nhuge;
-                    need_rec = true;
-                }
-            }
+        double coef[NP];
+        if (DEPOSIT) {
+#pragma unroll
+            for (int k = 0; k < NP; ++k) coef[k] = p.prop[k][i];
         }
-        if (need_rec && DEPOSIT) {
-            const double nrm = kernel_norm(p.kernel_id, h);
-            Rec r;
-            r.pa = pa0; r.pb = pb0; r.inv_h = (float)(1.0 / h); r.pad = 0.f;
-            for (int k = 0; k < AST_MAX_PROPS; ++k) r.c[k] = k < p.n_prop ? (float)(p.prop[k][i] * nrm) : 0.f;
-            rec[i] = r;
-        }
+        bin_particle<SHAPE, DEPOSIT, NP>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
     }
     // one reduction for both counts: per block pairs <= 256 * 9 * 256 < 2^20 and large-h entries <= 256 * 9 < 2^12
     const uint32_t packed = block_sum_u32((nhuge << 20) | npairs, red);
     if (threadIdx.x == 0) {
-        block_pairs[blockIdx.x] = packed & 0xfffffu;
-        block_huge[blockIdx.x] = packed >> 20;
+        block_pairs[blk] = packed & 0xfffffu;
+        block_huge[blk] = packed >> 20;
+    }
+}
+
+// ---- TMA-staged K1 -------------------------------------------------------------------------------------------------
+// Persistent CTAs stream the particle arrays through shared memory with 1-D bulk copies (cp.async.bulk, the TMA engine)
+// signalled on mbarriers, two stages deep: while the CTA works on particle block b the copies of block b + gridDim are
+// already in flight, so HBM latency is hidden independently of occupancy.  Only full blocks of 256 particles go through
+// here (16-byte alignment of every copy); the tail block uses bin_kernel.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int NP>
+struct __align__(128) BinStage {
+    double pos[3 * kBinThreads];
+    double h[kBinThreads];
+    double prop[NP][kBinThreads];
+};
+
+template <int SHAPE, int NP>
+__global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
+                                                              uint64_t *__restrict__ block_huge, int64_t n_full_blocks)
+{
+    __shared__ BinStage<NP> st[2];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t red[34];
+    const int tid = threadIdx.x;
+    constexpr uint32_t kBytes = (uint32_t)sizeof(BinStage<NP>);
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t blk, int s) {          // one elected thread: arm the barrier, launch the bulk copies
+        mbar_expect_tx(&bar[s], kBytes);
+        const int64_t i0 = blk * kBinThreads;
+        tma_load_1d(st[s].pos, p.pos + 3 * i0, 3 * kBinThreads * 8, &bar[s]);
+        tma_load_1d(st[s].h, p.h + i0, kBinThreads * 8, &bar[s]);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) tma_load_1d(st[s].prop[k], p.prop[k] + i0, kBinThreads * 8, &bar[s]);
+    };
+    int64_t blk = blockIdx.x;
+    if (tid == 0 && blk < n_full_blocks) issue(blk, 0);
+    uint32_t phase[2] = { 0u, 0u };
+    for (int it = 0; blk < n_full_blocks; blk += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int64_t next = blk + gridDim.x;
+        if (tid == 0 && next < n_full_blocks) issue(next, s ^ 1);     // stage s^1 was released by the barrier below
+        mbar_wait(&bar[s], phase[s]);
+        phase[s] ^= 1u;
+        const int64_t i = blk * kBinThreads + tid;
+        const double pa0 = st[s].pos[3 * tid + p.a_col], pb0 = st[s].pos[3 * tid + p.b_col], h = st[s].h[tid];
+        double coef[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) coef[k] = st[s].prop[k][tid];
+        uint32_t npairs = 0, nhuge = 0;
+        bin_particle<SHAPE, true, NP>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
+        const uint32_t packed = block_sum_u32((nhuge << 20) | npairs, red);     // contains the CTA barriers that release stage s
+        if (tid == 0) {
+            block_pairs[blk] = packed & 0xfffffu;
+            block_huge[blk] = packed >> 20;
+        }
     }
 }
 
@@ -412,7 +523,7 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
     int since_fold = 0;
     for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t j = base + lane;
-        bool hit = false;
+        bool hit = false, outer = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 C = make_float2(0.f, 0.f);
         if (j < total) {
@@ -432,19 +543,24 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
             const float sx = dxf * r.inv_h, sy = dyf * r.inv_h;
             const float ddx = fmaxf(fmaxf(lox - fx, fx - hix), 0.f) * sx;
             const float ddy = fmaxf(fmaxf(loy - fy, fy - hiy), 0.f) * sy;
-            hit = ddx * ddx + ddy * ddy < 4.0001f;
+            const float qmin2 = ddx * ddx + ddy * ddy;          // squared distance (in h) from the particle to the sub-tile
+            hit = qmin2 < 4.0001f;
+            outer = hit && SHAPE == SHAPE_CUBIC && qmin2 >= 1.0f;   // every pixel of the sub-tile has q >= 1: f = 2 a^3 only
             P = make_float4(fx * sx, fy * sy, sx, sy);
             C = make_float2(r.c[0], NP > 1 ? r.c[1] : 0.f);
         }
-        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        // full hits are compacted from the front of the warp's 32 slots, outer-annulus hits from the back
+        const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
+        const unsigned ball_o = __ballot_sync(0xffffffffu, outer);
         if (hit) {
-            const int dst = __popc(ball & ((1u << lane) - 1u));
+            const unsigned lt = (1u << lane) - 1u;
+            const int dst = outer ? 31 - __popc(ball_o & lt) : __popc(ball_f & lt);
             sP[warp][dst] = P;
             sC[warp][dst] = C;
         }
         __syncwarp();
-        const int nh = __popc(ball);
-        for (int e = 0; e < nh; ++e) {
+        const int nf = __popc(ball_f), no = __popc(ball_o), nh = nf + no;
+        for (int e = 0; e < nf; ++e) {
             const float4 q = sP[warp][e];
             const float2 c = sC[warp][e];
             float ax2[PX], by2[PY];
@@ -460,6 +576,27 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
                     acc[0][ix * PY + iy] = fmaf(c.x, f, acc[0][ix * PY + iy]);
                     if (NP > 1) acc[NP - 1][ix * PY + iy] = fmaf(c.y, f, acc[NP - 1][ix * PY + iy]);
                 }
+        }
+        if (SHAPE == SHAPE_CUBIC) {
+            for (int e = 32 - no; e < 32; ++e) {
+                const float4 q = sP[warp][e];
+                float2 c = sC[warp][e];
+                c.x += c.x; c.y += c.y;                          // the factor 2 of f = 2 a^3
+                float ax2[PX], by2[PY];
+#pragma unroll
+                for (int i = 0; i < PX; ++i) { const float t = fmaf(-xf[i], q.z, q.x); ax2[i] = t * t; }
+#pragma unroll
+                for (int i = 0; i < PY; ++i) { const float t = fmaf(-yf[i], q.w, q.y); by2[i] = t * t; }
+#pragma unroll
+                for (int ix = 0; ix < PX; ++ix)
+#pragma unroll
+                    for (int iy = 0; iy < PY; ++iy) {
+                        const float a1 = __saturatef(fmaf(fast_sqrt(ax2[ix] + by2[iy]), -0.5f, 1.0f));
+                        const float f = a1 * a1 * a1;
+                        acc[0][ix * PY + iy] = fmaf(c.x, f, acc[0][ix * PY + iy]);
+                        if (NP > 1) acc[NP - 1][ix * PY + iy] = fmaf(c.y, f, acc[NP - 1][ix * PY + iy]);
+                    }
+            }
         }
         __syncwarp();
         since_fold += nh;
@@ -541,6 +678,7 @@ struct Layout2 {
     int64_t ntiles;
     int64_t pair_cap, huge_cap;
     uint64_t *block_pairs, *block_huge;   // nb + 1 each
+    uint64_t *scan_tmp;
     Rec *rec;
     uint64_t *pairs_a, *pairs_b, *huge;
     uint32_t *tbeg, *tend;
@@ -575,6 +713,7 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     Carver c(ws);
     L.block_pairs = c.take<uint64_t>(L.nb + 1);
     L.block_huge = c.take<uint64_t>(L.nb + 1);
+    L.scan_tmp = c.take<uint64_t>(2 * scan_num_blocks(L.nb + 1) + 2);
     L.rec = c.take<Rec>(p->n > 0 ? p->n : 1);
     L.pairs_a = c.take<uint64_t>(L.pair_cap);
     L.pairs_b = c.take<uint64_t>(L.pair_cap);
@@ -596,6 +735,8 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     a.n_prop = p->n_prop;
     a.kernel_id = p->kernel_id;
     a.shape = kernel_shape(p->kernel_id);
+    a.norm_c = kernel_norm(p->kernel_id, 1.0);
+    a.norm_dim = (p->kernel_id == 0 || p->kernel_id == 2) ? 3 : 2;
     a.ax = make_axis(p->x_min, p->x_max, p->nx);
     a.ay = make_axis(p->y_min, p->y_max, p->ny);
     a.ntx = (p->nx + TILE - 1) / TILE;
@@ -679,13 +820,45 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     uint64_t totals[2] = { 0, 0 };
     if (p->n > 0) {
         tk.begin(0);
-        if (a.shape == SHAPE_CUBIC) bin_kernel<SHAPE_CUBIC, true><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
-        else bin_kernel<SHAPE_WENDLAND, true><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        {
+            // full blocks through the TMA-staged persistent kernel when every bulk copy is 16-byte aligned, the tail
+            // block (and everything, when AST_BIN_TMA=0 or a pointer is misaligned) through the plain kernel
+            bool aligned = ((uintptr_t)pos % 16 == 0) && ((uintptr_t)h % 16 == 0);
+            for (int k = 0; k < p->n_prop; ++k) aligned = aligned && ((uintptr_t)prop[k] % 16 == 0);
+            static int use_tma = -1;
+            if (use_tma < 0) { const char *e = getenv("AST_BIN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+            const int64_t n_full = (aligned && use_tma) ? p->n / kBinThreads : 0;
+            if (n_full > 0) {
+                int dev = 0, sm = 148;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+                // persistent grid: one wave of resident CTAs (multiple of the SM count)
+#define AST_LAUNCH_TMA(SH, NPV)                                                                                         \
+    do {                                                                                                                \
+        int per_sm = 1;                                                                                                 \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_tma_kernel<SH, NPV>, kBinThreads, 0);                \
+        int64_t grid = (int64_t)sm * (per_sm > 0 ? per_sm : 1);                                                         \
+        if (grid > n_full) grid = n_full;                                                                               \
+        bin_tma_kernel<SH, NPV><<<(unsigned)grid, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full);  \
+    } while (0)
+                if (a.shape == SHAPE_CUBIC) { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_CUBIC, 1); else AST_LAUNCH_TMA(SHAPE_CUBIC, 2); }
+                else { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_WENDLAND, 1); else AST_LAUNCH_TMA(SHAPE_WENDLAND, 2); }
+#undef AST_LAUNCH_TMA
+                st.n_launches += 1;
+            }
+            const int64_t n_rest = L.nb - n_full;
+            if (n_rest > 0) {
+#define AST_LAUNCH_BIN(SH, NPV) bin_kernel<SH, true, NPV><<<(unsigned)n_rest, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full)
+                if (a.shape == SHAPE_CUBIC) { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_CUBIC, 1); else AST_LAUNCH_BIN(SHAPE_CUBIC, 2); }
+                else { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_WENDLAND, 1); else AST_LAUNCH_BIN(SHAPE_WENDLAND, 2); }
+#undef AST_LAUNCH_BIN
+                st.n_launches += 1;
+            }
+        }
         tk.end();
         tk.begin(1);
-        scan2_exclusive_kernel<uint64_t><<<2, kScanThreads, 0, s>>>(L.block_pairs, L.block_huge, L.nb + 1);
+        { int nl = 0; AST_CUDA_TRY(scan2_exclusive<uint64_t>(L.block_pairs, L.block_huge, L.nb + 1, L.scan_tmp, s, &nl)); st.n_launches += nl; }
         tk.end();
-        st.n_launches += 2;
         AST_CUDA_TRY(cudaGetLastError());
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -775,7 +948,7 @@ extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
     if (p->n > 0) {
         if (bbox || cls) bbox_cls_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, bbox, cls);
-        bin_kernel<SHAPE_CUBIC, false><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        bin_kernel<SHAPE_CUBIC, false, 1><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, 0);
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
         AST_CUDA_TRY(cudaGetLastError());

@@ -212,6 +212,82 @@ inline cudaError_t scan_exclusive(T *data, int64_t n, T *tmp, T *total_out, cuda
     return cudaGetLastError();
 }
 
+
+// ---- two arrays, multi-block: blockIdx.y selects the array.  sums: 2 * scan_num_blocks(n) entries.
+template <class T>
+__global__ void __launch_bounds__(kScanThreads) scan2_block_sums_kernel(const T *__restrict__ a, const T *__restrict__ b, int64_t n,
+                                                                        T *__restrict__ sums)
+{
+    __shared__ T sm[32];
+    const T *data = blockIdx.y == 0 ? a : b;
+    const int64_t i0 = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) s += (i0 + k < n) ? data[i0 + k] : (T)0;
+    T t = block_reduce_sum<T>(s, sm);
+    if (threadIdx.x == 0) sums[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kScanThreads) scan2_apply_kernel(T *__restrict__ a, T *__restrict__ b, int64_t n,
+                                                                   const T *__restrict__ base)
+{
+    __shared__ T warp_sum[32];
+    T *data = blockIdx.y == 0 ? a : b;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * kScanTile + (int64_t)tid * kScanItems;
+    T v[kScanItems];
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (i0 + k < n) ? data[i0 + k] : (T)0;
+        s += v[k];
+    }
+    T inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = warp_sum[lane];
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_sum[lane] = winc - w;
+    }
+    __syncthreads();
+    T excl = base[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] + warp_sum[warp] + (inc - s);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (i0 + k < n) data[i0 + k] = excl;
+        excl += v[k];
+    }
+}
+
+// exclusive scan of a[0..n) and b[0..n) in place.  tmp: 2 * scan_num_blocks(n) elements.
+template <class T>
+inline cudaError_t scan2_exclusive(T *a, T *b, int64_t n, T *tmp, cudaStream_t s, int *launches = nullptr)
+{
+    if (n <= 0) return cudaSuccess;
+    const int64_t nb = scan_num_blocks(n);
+    if (nb <= 2) {
+        scan2_exclusive_kernel<T><<<2, kScanThreads, 0, s>>>(a, b, n);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    scan2_block_sums_kernel<T><<<dim3((unsigned)nb, 2), kScanThreads, 0, s>>>(a, b, n, tmp);
+    scan2_exclusive_kernel<T><<<2, kScanThreads, 0, s>>>(tmp, tmp + nb, nb);
+    scan2_apply_kernel<T><<<dim3((unsigned)nb, 2), kScanThreads, 0, s>>>(a, b, n, tmp);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 constexpr int kSortWarps = 8;
 constexpr int kSortWarpItems = 1024;

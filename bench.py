@@ -334,7 +334,8 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             t = e0.elapsed_time(e1) / 3
-            sweep.append({"h_scale": sc, "support_radius_px": float(2 * hs.mean().item() * args.npix), "ms": t,
+            eng.project(pos_d, hs, props_d, size, CoordinateAxes.Z, bounds, out=out, timing=True)
+            sweep.append({"h_scale": sc, "stage_ms": [round(x, 4) for x in eng.last_stats["stage_ms"]], "support_radius_px": float(2 * hs.mean().item() * args.npix), "ms": t,
                           "particles_per_s": N / (t * 1e-3), "hbm_frac": alg_bytes / (t * 1e-3) / 1e9 / peak,
                           "pairs": eng.last_stats["n_pairs"]})
 

@@ -143,7 +143,10 @@ def test_subpixel_regime_exact_support(oracle):
         m, st = gpu_project(pos, h, prop, (npix, npix), 2, (0.0, 10.0, 0.0, 10.0), periodic=periodic, box=box)
         assert st["n_pairs"] == 0
         check(m, ref)
-        assert np.array_equal(m != 0, cnt > 0)
+        assert not (m != 0)[cnt == 0].any()                     # never deposits outside the reference mask
+        # the float32 shape function gives exactly 0 for q within ~1e-7 of 2 (e.g. h = d/2 particles sitting on a pixel
+        # corner: their four neighbours are at r = 2h up to rounding); the reference deposits W ~ 1e-45 there
+        assert not ((m == 0) & (ref > 1e-25 * ref.max())).any()
 
 
 def test_properties_linearity_permutation(oracle):
