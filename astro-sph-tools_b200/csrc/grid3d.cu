@@ -19,11 +19,10 @@ namespace ast {
 constexpr int BRICK = AST_BRICK;
 constexpr int kBin3Threads = 256;
 constexpr int kAcc3Threads = 128;
-constexpr int kChunk3 = 128;
 
 struct __align__(32) Rec3 {
     double x, y, z;
-    float h, c;
+    float inv_h, c;            // 1/h and prop * norm(h), narrowed once per particle
 };
 static_assert(sizeof(Rec3) == 32, "record is one 32-byte sector");
 
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
         if (need_rec && DEPOSIT) {
             Rec3 r;
             r.x = x0[0]; r.y = x0[1]; r.z = x0[2];
-            r.h = (float)h;
+            r.inv_h = (float)(1.0 / h);
             r.c = (float)(p.prop[i] * kernel_norm(p.kernel_id, h));
             rec[i] = r;
         }
@@ -174,13 +173,16 @@ struct Acc3 {
     double box[3];
 };
 
+// One CTA per brick, four autonomous warps (no CTA barrier): warp w owns the 4x4x8 column (x,y quadrant) of the brick and
+// walks the brick's list on its own, 32 entries at a time: every lane stages one entry (float64 -> brick-relative float32),
+// tests it against the warp's column, hits are compacted into the warp's shared-memory slots with a ballot (entries whose
+// column lies wholly in the outer annulus q >= 1 of the cubic spline go to a second, cheaper loop), then every lane
+// evaluates the hits for its 4 voxels (contiguous in z).
 template <int SHAPE>
 __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
 {
-    __shared__ float4 sP[kChunk3];      // {ux*sx, uy*sy, uz*sz, c}
-    __shared__ float4 sS[kChunk3];      // {sx, sy, sz, warp mask}
-    __shared__ int s_cnt[4];
-
+    __shared__ float4 sP[4][32];        // {ux*sx, uy*sy, uz*sz, c}
+    __shared__ float4 sS[4][32];        // {sx, sy, sz, -}
     const int brick = blockIdx.x;
     const uint32_t beg = a.tbeg[brick], cnt = a.tend[brick] - beg;
     const uint32_t total = cnt + a.n_huge;
@@ -188,19 +190,21 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bz = brick % a.nb[2], by = (brick / a.nb[2]) % a.nb[1], bx = brick / (a.nb[2] * a.nb[1]);
     const int X0 = bx * BRICK, Y0 = by * BRICK, Z0 = bz * BRICK;
-    // warp -> 4x4 column (x,y quadrant), lane -> (lx, ly, z half); 4 voxels contiguous in z per thread
     const int xl = 4 * (warp >> 1) + (lane >> 3);
     const int yl = 4 * (warp & 1) + ((lane >> 1) & 3);
     const int zl = 4 * (lane & 1);
     const float xf = (float)xl, yf = (float)yl;
     const float zf0 = (float)zl, zf1 = (float)(zl + 1), zf2 = (float)(zl + 2), zf3 = (float)(zl + 3);
+    const float lox = 4.f * (float)(warp >> 1), loy = 4.f * (float)(warp & 1);
+    const float d0 = (float)a.d[0], d1 = (float)a.d[1], d2 = (float)a.d[2];
     float acc[4] = { 0.f, 0.f, 0.f, 0.f };
     double acc64[4] = { 0.0, 0.0, 0.0, 0.0 };
+    int since_fold = 0;
 
-    for (uint32_t base = 0; base < total; base += kChunk3) {
-        const uint32_t j = base + tid;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        bool hit = false, outer = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f), S = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t mask = 0;
         if (j < total) {
             uint32_t idx, m;
             if (j < cnt) {
@@ -216,40 +220,29 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
             const float fx = (float)((r.x + image_shift3(a.n_img, a.box, (int)m, 0) - a.lo[0]) * a.inv_d[0] - (double)X0);
             const float fy = (float)((r.y + image_shift3(a.n_img, a.box, (int)m, 1) - a.lo[1]) * a.inv_d[1] - (double)Y0);
             const float fz = (float)((r.z + image_shift3(a.n_img, a.box, (int)m, 2) - a.lo[2]) * a.inv_d[2] - (double)Z0);
-            const double inv_h = 1.0 / (double)r.h;
-            const float sx = (float)(a.d[0] * inv_h), sy = (float)(a.d[1] * inv_h), sz = (float)(a.d[2] * inv_h);
-            P = make_float4(fx * sx, fy * sy, fz * sz, r.c);
+            const float sx = d0 * r.inv_h, sy = d1 * r.inv_h, sz = d2 * r.inv_h;
+            const float ddx = fmaxf(fmaxf(lox - fx, fx - (lox + 3.f)), 0.f) * sx;
+            const float ddy = fmaxf(fmaxf(loy - fy, fy - (loy + 3.f)), 0.f) * sy;
             const float ddz = fmaxf(fmaxf(-fz, fz - 7.f), 0.f) * sz;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float lox = 4.f * (float)(w >> 1), loy = 4.f * (float)(w & 1);
-                const float ddx = fmaxf(fmaxf(lox - fx, fx - (lox + 3.f)), 0.f) * sx;
-                const float ddy = fmaxf(fmaxf(loy - fy, fy - (loy + 3.f)), 0.f) * sy;
-                if (ddx * ddx + ddy * ddy + ddz * ddz < 4.0001f) mask |= 1u << w;
-            }
-            S = make_float4(sx, sy, sz, __uint_as_float(mask));
+            const float qmin2 = ddx * ddx + ddy * ddy + ddz * ddz;
+            hit = qmin2 < 4.0001f;
+            outer = hit && SHAPE == SHAPE_CUBIC && qmin2 >= 1.0f;
+            P = make_float4(fx * sx, fy * sy, fz * sz, r.c);
+            S = make_float4(sx, sy, sz, 0.f);
         }
-        const unsigned ball = __ballot_sync(0xffffffffu, mask != 0);
-        __syncthreads();
-        if (lane == 0) s_cnt[warp] = __popc(ball);
-        __syncthreads();
-        int off = 0, nc = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int c = s_cnt[w];
-            off += w < warp ? c : 0;
-            nc += c;
+        const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
+        const unsigned ball_o = __ballot_sync(0xffffffffu, outer);
+        if (hit) {
+            const unsigned lt = (1u << lane) - 1u;
+            const int dst = outer ? 31 - __popc(ball_o & lt) : __popc(ball_f & lt);
+            sP[warp][dst] = P;
+            sS[warp][dst] = S;
         }
-        if (mask != 0) {
-            const int dst = off + __popc(ball & ((1u << lane) - 1u));
-            sP[dst] = P;
-            sS[dst] = S;
-        }
-        __syncthreads();
-        for (int e = 0; e < nc; ++e) {
-            const float4 s = sS[e];
-            if (!((__float_as_uint(s.w) >> warp) & 1u)) continue;
-            const float4 q = sP[e];
+        __syncwarp();
+        const int nf = __popc(ball_f), no = __popc(ball_o);
+        for (int e = 0; e < nf; ++e) {
+            const float4 s = sS[warp][e];
+            const float4 q = sP[warp][e];
             const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
             const float axy = fmaf(by2, by2, ax * ax);
             const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
@@ -258,15 +251,38 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
             acc[2] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c2, c2, axy))), acc[2]);
             acc[3] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c3, c3, axy))), acc[3]);
         }
+        if (SHAPE == SHAPE_CUBIC) {
+            for (int e = 32 - no; e < 32; ++e) {
+                const float4 s = sS[warp][e];
+                const float4 q = sP[warp][e];
+                const float cc = q.w + q.w;                       // the factor 2 of f = 2 a^3
+                const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
+                const float axy = fmaf(by2, by2, ax * ax);
+                const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
+                float a0 = __saturatef(fmaf(fast_sqrt(fmaf(c0, c0, axy)), -0.5f, 1.0f));
+                float a1 = __saturatef(fmaf(fast_sqrt(fmaf(c1, c1, axy)), -0.5f, 1.0f));
+                float a2 = __saturatef(fmaf(fast_sqrt(fmaf(c2, c2, axy)), -0.5f, 1.0f));
+                float a3 = __saturatef(fmaf(fast_sqrt(fmaf(c3, c3, axy)), -0.5f, 1.0f));
+                acc[0] = fmaf(cc, a0 * a0 * a0, acc[0]);
+                acc[1] = fmaf(cc, a1 * a1 * a1, acc[1]);
+                acc[2] = fmaf(cc, a2 * a2 * a2, acc[2]);
+                acc[3] = fmaf(cc, a3 * a3 * a3, acc[3]);
+            }
+        }
+        __syncwarp();
+        since_fold += nf + no;
+        if (since_fold >= 96) {
+            since_fold = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { acc64[k] += (double)acc[k]; acc[k] = 0.f; }
+            for (int k = 0; k < 4; ++k) { acc64[k] += (double)acc[k]; acc[k] = 0.f; }
+        }
     }
     const int xi = X0 + xl, yi = Y0 + yl;
     if (xi < a.n[0] && yi < a.n[1]) {
         double *row = a.out + ((size_t)xi * a.n[1] + yi) * a.n[2];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (Z0 + zl + k < a.n[2]) row[Z0 + zl + k] += acc64[k];
+            if (Z0 + zl + k < a.n[2]) row[Z0 + zl + k] += acc64[k] + (double)acc[k];
     }
 }
 
