@@ -47,12 +47,12 @@ def create_images_sharded(positions, smoothing_lengths, particle_properties, ima
     kernel = kernel_id_of(kernel_func if kernel_func is not None else quartic_spline_kernel)
     positions, smoothing_lengths, props = _validate(positions, smoothing_lengths, list(particle_properties))
     eng = default_projector()
-    dev = eng.device
-    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-    part = eng.project(to_dev(positions), to_dev(smoothing_lengths), [to_dev(q) for q in props], image_size, projection_axis,
-                       (x_min, x_max, y_min, y_max), kernel, periodic, box_size)
+    part = eng.project_host(positions, smoothing_lengths, props, image_size, projection_axis, (x_min, x_max, y_min, y_max),
+                            kernel, periodic, box_size, return_device=True)
     part = reduce_maps(part, dst, group, all_ranks)
     rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
     if all_ranks or rank == dst:
-        return part.cpu().numpy()
+        host = torch.empty(part.shape, dtype=part.dtype, pin_memory=True)
+        host.copy_(part)
+        return host.numpy()
     return None

@@ -116,14 +116,71 @@ class Projector2D:
 
     # ---- host call (numpy in, numpy out): what create_image uses -------------------------------------------
     def project_host(self, positions, smoothing_lengths, props, image_size, axis, bounds, kernel="cubic_spline_3d",
-                     periodic=False, box=None, stream=None):
+                     periodic=False, box=None, stream=None, batch_particles=1 << 22, return_device=False):
+        """Host arrays in, host map out.  The particle arrays are streamed to the device in batches of
+        `batch_particles` through two staging buffers on a copy stream, so the host-to-device transfer of batch b+1
+        overlaps the deposition of batch b (deposition is linear in particles: batches accumulate into the same map).
+        Pinned host arrays make the copies truly asynchronous; pageable ones still overlap with the running kernels."""
         torch = self.torch
         single = not isinstance(props, (list, tuple))
         plist = [props] if single else list(props)
         dev = self.device
-        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-        pos_d, h_d = to_dev(positions), to_dev(smoothing_lengths)
-        props_d = [to_dev(q) for q in plist]
-        out = self.project(pos_d, h_d, props_d[0] if single else props_d, image_size, axis, bounds, kernel, periodic, box,
-                           stream=stream)
-        return out.cpu().numpy()
+        n = int(positions.shape[0])
+        nb = max(1, min(16, -(-n // int(batch_particles)))) if n > 0 else 1
+        if nb == 1:
+            to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+            pos_d, h_d = to_dev(positions), to_dev(smoothing_lengths)
+            props_d = [to_dev(q) for q in plist]
+            out = self.project(pos_d, h_d, props_d[0] if single else props_d, image_size, axis, bounds, kernel, periodic, box,
+                               stream=stream)
+        else:
+            positions = np.ascontiguousarray(positions)
+            smoothing_lengths = np.ascontiguousarray(smoothing_lengths)
+            plist = [np.ascontiguousarray(q) for q in plist]
+            bn = -(-n // nb)
+            with torch.cuda.device(dev):
+                compute = stream if stream is not None else torch.cuda.current_stream()
+                if getattr(self, "_copy_stream", None) is None:
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                copy = self._copy_stream
+                key = (bn, len(plist))
+                if getattr(self, "_stage_key", None) != key:
+                    self._stage = [dict(pos=torch.empty((bn, 3), dtype=torch.float64, device=dev),
+                                        h=torch.empty(bn, dtype=torch.float64, device=dev),
+                                        props=[torch.empty(bn, dtype=torch.float64, device=dev) for _ in plist]) for _ in range(2)]
+                    self._stage_key = key
+                ready = [torch.cuda.Event(), torch.cuda.Event()]
+                free = [torch.cuda.Event(), torch.cuda.Event()]
+                out = torch.empty((len(plist), int(image_size[0]), int(image_size[1])), dtype=torch.float64, device=dev)
+                copy.wait_stream(compute)
+                n_launch = 0
+                for b in range(nb):
+                    lo, hi = b * bn, min(n, (b + 1) * bn)
+                    m = hi - lo
+                    if m <= 0:
+                        break
+                    k = b & 1
+                    st = self._stage[k]
+                    with torch.cuda.stream(copy):
+                        if b >= 2:
+                            copy.wait_event(free[k])
+                        st["pos"][:m].copy_(torch.from_numpy(positions[lo:hi]), non_blocking=True)
+                        st["h"][:m].copy_(torch.from_numpy(smoothing_lengths[lo:hi]), non_blocking=True)
+                        for dst, src in zip(st["props"], plist):
+                            dst[:m].copy_(torch.from_numpy(src[lo:hi]), non_blocking=True)
+                        ready[k].record(copy)
+                    compute.wait_event(ready[k])
+                    self.project(st["pos"][:m], st["h"][:m], [q[:m] for q in st["props"]], image_size, axis, bounds, kernel,
+                                 periodic, box, out=out, accumulate=b > 0, stream=compute)
+                    n_launch += self.last_stats["n_launches"]
+                    free[k].record(compute)
+                self.last_stats["n_launches"] = n_launch
+                self.last_stats["n_batches"] = nb
+            out = out[0] if single else out
+        if return_device:
+            return out
+        # device -> pinned host block (from torch's caching host allocator, so no page faults and full PCIe rate); the
+        # numpy array returned is a view that owns the block, i.e. a fresh array for the caller like the reference's
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out)
+        return host.numpy()

@@ -125,6 +125,19 @@ def test_edge_cases(oracle):
     check(m, ref)
 
 
+def test_batched_host_pipeline_matches_single_batch(oracle):
+    """project_host streams the particles in batches (H2D of batch b+1 overlaps the deposit of batch b)"""
+    from astro_sph_tools_b200.tools.projections import Projector2D
+    pos, h, prop = random_cloud(15, 7001, h_hi=0.9, signed=True)
+    ref = oracle.project2d(pos, h, np.stack([prop, 2 * prop]), (80, 80), 2, 0.0, 10.0, 0.0, 10.0)
+    eng = Projector2D()
+    one = eng.project_host(pos, h, [prop, 2 * prop], (80, 80), 2, (0.0, 10.0, 0.0, 10.0))
+    many = eng.project_host(pos, h, [prop, 2 * prop], (80, 80), 2, (0.0, 10.0, 0.0, 10.0), batch_particles=1000)
+    assert eng.last_stats["n_batches"] == 8
+    check(one[0], ref[0]); check(many[1], ref[1])
+    assert rel_l2(many, one) < 1e-7           # only the float32 partial-sum grouping differs between batchings
+
+
 def test_subpixel_regime_exact_support(oracle):
     """HBM-bound regime: supports below one pixel, particles on pixel corners; the direct-deposit path applies the exact
     float64 mask, so the set of non-zero pixels must equal the oracle's contributor mask"""
