@@ -15,6 +15,7 @@ MAX_PROPS = 2
 TILE = 32
 
 KERNEL_IDS = {"cubic_spline_3d": 0, "wendland_c2_2d": 1, "wendland_c2_3d": 2, "cubic_spline_2d": 3}
+KERNEL_TABLE = 4
 
 
 class Project2DParams(C.Structure):
@@ -23,7 +24,8 @@ class Project2DParams(C.Structure):
                 ("x_min", C.c_double), ("x_max", C.c_double), ("y_min", C.c_double), ("y_max", C.c_double),
                 ("box_a", C.c_double), ("box_b", C.c_double),
                 ("small_max_px", C.c_int64), ("huge_min_tiles", C.c_int64),
-                ("pair_capacity", C.c_int64), ("huge_capacity", C.c_int64)]
+                ("pair_capacity", C.c_int64), ("huge_capacity", C.c_int64),
+                ("kernel_table", C.c_void_p), ("kernel_table_n", C.c_int32), ("kernel_dim", C.c_int32)]
 
 
 class Project2DStats(C.Structure):
@@ -36,7 +38,8 @@ class Grid3DParams(C.Structure):
                 ("flags", C.c_int32), ("reserved", C.c_int32),
                 ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("box", C.c_double * 3),
                 ("small_max_vox", C.c_int64), ("huge_min_bricks", C.c_int64),
-                ("pair_capacity", C.c_int64), ("huge_capacity", C.c_int64)]
+                ("pair_capacity", C.c_int64), ("huge_capacity", C.c_int64),
+                ("kernel_table", C.c_void_p), ("kernel_table_n", C.c_int32), ("kernel_dim", C.c_int32)]
 
 
 class KnnParams(C.Structure):
@@ -54,7 +57,7 @@ _lib = None
 # every symbol include/astro_sph_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = ["ast_project2d_workspace_bytes", "ast_project2d", "ast_bin2d", "ast_contrib_count2d", "ast_kernel_eval",
            "ast_sort_workspace_bytes", "ast_radix_sort_u64", "ast_grid3d_workspace_bytes", "ast_grid3d", "ast_bin3d",
-           "ast_knn_workspace_bytes", "ast_knn_h", "ast_last_error", "ast_abi_version", "ast_tile_size",
+           "ast_knn_workspace_bytes", "ast_knn_h", "ast_knn_query", "ast_last_error", "ast_abi_version", "ast_tile_size",
            "ast_device_sm_count"]
 
 

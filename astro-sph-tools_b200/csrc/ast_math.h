@@ -2,16 +2,28 @@
 //   W(r,h) = norm(h) * f(q),  q = r/h,  support q < 2  (hard mask of the reference, _pixel_calculations.pyx:31)
 // Reference kernel: tools/projections/_kernels.pyx:15-19 (M4 cubic spline, 1/(pi h^3)).
 #pragma once
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+struct float2 { float x, y; };
+#endif
 #include "ast_geom.h"
 
 namespace ast {
 
 constexpr double kPi = 3.14159265358979323846;
 
-enum : int { SHAPE_CUBIC = 0, SHAPE_WENDLAND = 1 };
+enum : int { SHAPE_CUBIC = 0, SHAPE_WENDLAND = 1, SHAPE_TABLE = 2 };
 
-AST_HD bool kernel_valid(int kid) { return kid >= 0 && kid <= 3; }
-AST_HD int kernel_shape(int kid) { return (kid == 1 || kid == 2) ? SHAPE_WENDLAND : SHAPE_CUBIC; }
+// tabulated shape f(q) on q in [0,2]: n intervals, entry j = {f(q_j), f(q_j+1) - f(q_j)}, q_j = 2j/n (device pointer)
+struct ShapeTab {
+    const float2 *tab;
+    float scale;      // n / 2
+    int n;
+};
+
+AST_HD bool kernel_valid(int kid) { return kid >= 0 && kid <= 4; }     // 4 = AST_KERNEL_TABLE (deposition only)
+AST_HD int kernel_shape(int kid) { return kid == 4 ? SHAPE_TABLE : ((kid == 1 || kid == 2) ? SHAPE_WENDLAND : SHAPE_CUBIC); }
 
 // norm(h) for the shape functions below
 AST_HD double kernel_norm(int kid, double h)
@@ -61,10 +73,18 @@ __device__ __forceinline__ float shape_wendland(float q)
     float a2 = a * a;
     return (a2 * a2) * fmaf(q, 2.0f, 1.0f);
 }
-template <int SHAPE>
-__device__ __forceinline__ float shape_eval(float q)
+// linear interpolation in the table; exactly 0 for q >= 2 (the reference's hard mask)
+__device__ __forceinline__ float shape_table(float q, const ShapeTab &t)
 {
-    return SHAPE == SHAPE_CUBIC ? shape_cubic(q) : shape_wendland(q);
+    const float x = q * t.scale;
+    const int j = min((int)x, t.n - 1);
+    const float2 e = __ldg(t.tab + j);
+    return q < 2.0f ? fmaf(x - (float)j, e.y, e.x) : 0.0f;
+}
+template <int SHAPE>
+__device__ __forceinline__ float shape_eval(float q, const ShapeTab &t)
+{
+    return SHAPE == SHAPE_CUBIC ? shape_cubic(q) : (SHAPE == SHAPE_WENDLAND ? shape_wendland(q) : shape_table(q, t));
 }
 __device__ __forceinline__ float fast_sqrt(float x)
 {

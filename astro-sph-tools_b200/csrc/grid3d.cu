@@ -35,6 +35,9 @@ struct P3 {
     int nb[3];                       // bricks per axis
     int n_img, img_shift;
     double box[3];                   // periodic image m = 9*(ia+1) + 3*(ib+1) + (ic+1), shift = (ia,ib,ic) * box
+    ShapeTab tab;
+    double norm_c;
+    int norm_dim;
     int64_t small_max_vox, huge_min_bricks;
 };
 
@@ -46,6 +49,13 @@ __host__ __device__ __forceinline__ double image_shift3(int n_img, const double 
 {
     const int t = c == 0 ? m / 9 : (c == 1 ? (m / 3) % 3 : m % 3);
     return n_img == 1 ? 0.0 : (double)(t - 1) * box[c];
+}
+
+__device__ __forceinline__ double norm3(const P3 &p, double h)
+{
+    const double ih = 1.0 / h;
+    const double t = p.norm_c * ih * ih;
+    return p.norm_dim == 3 ? t * ih : t;
 }
 
 template <int SHAPE>
@@ -60,7 +70,7 @@ __device__ __forceinline__ void deposit_small3(const P3 &p, const Bin3 &b, const
             double *row = p.out + ((size_t)xi * ny + yi) * nz;
             for (int zi = b.lo[2]; zi <= b.hi[2]; ++zi) {
                 const double r2 = AST_DADD(dxy, dist2(p.ax[2], q[2], zi));
-                if (r2 < R2) atomicAdd(row + zi, coef * (double)shape_eval<SHAPE>(fast_sqrt((float)(r2 * inv_h2))));
+                if (r2 < R2) atomicAdd(row + zi, coef * (double)shape_eval<SHAPE>(fast_sqrt((float)(r2 * inv_h2)), p.tab));
             }
         }
     }
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
             const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
             Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
             if (b.cls == CLS_SMALL) {
-                if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * kernel_norm(p.kernel_id, h));
+                if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * norm3(p, h));
             } else if (b.cls == CLS_TILED) {
                 npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
                 need_rec = true;
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
             Rec3 r;
             r.x = x0[0]; r.y = x0[1]; r.z = x0[2];
             r.inv_h = (float)(1.0 / h);
-            r.c = (float)(p.prop[i] * kernel_norm(p.kernel_id, h));
+            r.c = (float)(p.prop[i] * norm3(p, h));
             rec[i] = r;
         }
     }
@@ -171,6 +181,7 @@ struct Acc3 {
     double lo[3], d[3], inv_d[3];
     int n[3], nb[3], img_shift, n_img;
     double box[3];
+    ShapeTab tab;
 };
 
 // One CTA per brick, four autonomous warps (no CTA barrier): warp w owns the 4x4x8 column (x,y quadrant) of the brick and
@@ -246,10 +257,10 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
             const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
             const float axy = fmaf(by2, by2, ax * ax);
             const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
-            acc[0] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c0, c0, axy))), acc[0]);
-            acc[1] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c1, c1, axy))), acc[1]);
-            acc[2] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c2, c2, axy))), acc[2]);
-            acc[3] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c3, c3, axy))), acc[3]);
+            acc[0] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c0, c0, axy)), a.tab), acc[0]);
+            acc[1] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c1, c1, axy)), a.tab), acc[1]);
+            acc[2] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c2, c2, axy)), a.tab), acc[2]);
+            acc[3] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c3, c3, axy)), a.tab), acc[3]);
         }
         if (SHAPE == SHAPE_CUBIC) {
             for (int e = 32 - no; e < 32; ++e) {
@@ -323,6 +334,9 @@ static int validate3(const ast_grid3d_params *p)
     const int64_t nbr = (int64_t)((p->nx + BRICK - 1) / BRICK) * ((p->ny + BRICK - 1) / BRICK) * ((p->nz + BRICK - 1) / BRICK);
     AST_REQUIRE(nbr < (1ll << 26), "grid too large (more than 2^26 bricks)");
     AST_REQUIRE(kernel_valid(p->kernel_id), "unknown kernel id %d", p->kernel_id);
+    if (p->kernel_id == AST_KERNEL_TABLE)
+        AST_REQUIRE(p->kernel_table != nullptr && p->kernel_table_n >= 2 && (p->kernel_dim == 2 || p->kernel_dim == 3),
+                    "AST_KERNEL_TABLE needs kernel_table (device), kernel_table_n >= 2 and kernel_dim 2 or 3");
     for (int c = 0; c < 3; ++c) AST_REQUIRE(p->hi[c] > p->lo[c], "empty or inverted grid bounds");
     if (p->flags & AST_FLAG_PERIODIC)
         for (int c = 0; c < 3; ++c) AST_REQUIRE(p->box[c] > 0, "periodic gridding needs box[0..2] > 0");
@@ -360,6 +374,11 @@ static P3 make_p3(const ast_grid3d_params *p, const double *pos, const double *h
     a.n = p->n;
     a.kernel_id = p->kernel_id;
     a.shape = kernel_shape(p->kernel_id);
+    a.norm_c = p->kernel_id == AST_KERNEL_TABLE ? 1.0 : kernel_norm(p->kernel_id, 1.0);
+    a.norm_dim = p->kernel_id == AST_KERNEL_TABLE ? p->kernel_dim : ((p->kernel_id == 0 || p->kernel_id == 2) ? 3 : 2);
+    a.tab.tab = (const float2 *)p->kernel_table;
+    a.tab.n = p->kernel_table_n;
+    a.tab.scale = 0.5f * (float)p->kernel_table_n;
     const int n3[3] = { p->nx, p->ny, p->nz };
     for (int c = 0; c < 3; ++c) {
         a.ax[c] = make_axis(p->lo[c], p->hi[c], n3[c]);
@@ -416,7 +435,8 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
     if (p->n > 0) {
         tk.begin(0);
         if (a.shape == SHAPE_CUBIC) bin3_kernel<SHAPE_CUBIC, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
-        else bin3_kernel<SHAPE_WENDLAND, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        else if (a.shape == SHAPE_WENDLAND) bin3_kernel<SHAPE_WENDLAND, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
+        else bin3_kernel<SHAPE_TABLE, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
         tk.end();
         tk.begin(1);
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
@@ -447,6 +467,7 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
         }
         c.img_shift = a.img_shift;
         c.n_img = a.n_img;
+        c.tab = a.tab;
         for (int k = 0; k < 3; ++k) c.box[k] = a.box[k];
         for (int64_t r = 0; r < rounds; ++r) {
             const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
@@ -468,7 +489,8 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
             c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
             tk.begin(5);
             if (a.shape == SHAPE_CUBIC) brick_accum_kernel<SHAPE_CUBIC><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
-            else brick_accum_kernel<SHAPE_WENDLAND><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
+            else if (a.shape == SHAPE_WENDLAND) brick_accum_kernel<SHAPE_WENDLAND><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
+            else brick_accum_kernel<SHAPE_TABLE><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
             tk.end();
             st.n_launches += 3 + nl;
             AST_CUDA_TRY(cudaGetLastError());

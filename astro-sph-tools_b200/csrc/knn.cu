@@ -32,6 +32,7 @@ struct KnnArgs {
     const uint32_t *sidx;        // cell order -> original index
     const uint32_t *cbeg, *cend;
     const uint32_t *qlist;       // nullable: sorted positions of the queries
+    const double *qpos;          // EXTERNAL queries: (nq,3) row-major positions, output row = query index
     int64_t nq, q_begin;
     int k;
     double *h_out;
@@ -109,13 +110,14 @@ struct Heap {
     }
 };
 
-template <int KCAP, bool WANT_IDX>
+template <int KCAP, bool WANT_IDX, bool EXTERNAL>
 __global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nq) return;
-    const int64_t s = a.qlist ? (int64_t)a.qlist[t] : t;
-    const double x = a.xs[s], y = a.ys[s], z = a.zs[s];
+    const int64_t s = EXTERNAL ? 0 : (a.qlist ? (int64_t)a.qlist[t] : t);
+    const double x = EXTERNAL ? a.qpos[3 * t] : a.xs[s], y = EXTERNAL ? a.qpos[3 * t + 1] : a.ys[s],
+                 z = EXTERNAL ? a.qpos[3 * t + 2] : a.zs[s];
     const KnnGrid &g = a.g;
     const int G = g.G;
     const bool per = g.box > 0.0;
@@ -177,8 +179,8 @@ __global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
         if (safe > 0.0 && hp.d[0] < safe * safe) break;
     }
 
-    const int64_t row = (int64_t)a.sidx[s] - a.q_begin;
-    a.h_out[row] = sqrt(hp.d[0]);
+    const int64_t row = EXTERNAL ? t : (int64_t)a.sidx[s] - a.q_begin;
+    if (a.h_out) a.h_out[row] = sqrt(hp.d[0]);
     if (WANT_IDX) {
         // heap-sort in place: ascending (d2, idx)
         const int k = a.k;
@@ -248,8 +250,48 @@ template <int KCAP>
 static void launch_query(const KnnArgs &a, bool want_idx, cudaStream_t s)
 {
     const unsigned nb = (unsigned)((a.nq + 127) / 128);
-    if (want_idx) knn_query_kernel<KCAP, true><<<nb, 128, 0, s>>>(a);
-    else knn_query_kernel<KCAP, false><<<nb, 128, 0, s>>>(a);
+    if (a.qpos) knn_query_kernel<KCAP, true, true><<<nb, 128, 0, s>>>(a);
+    else if (want_idx) knn_query_kernel<KCAP, true, false><<<nb, 128, 0, s>>>(a);
+    else knn_query_kernel<KCAP, false, false><<<nb, 128, 0, s>>>(a);
+}
+
+// builds the cell list of `pos` in the workspace (steps 1 and 2) and fills the grid / array part of KnnArgs
+static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout &L, bool subset, int64_t q_begin, int64_t q_end,
+                     cudaStream_t s, KnnArgs &a)
+{
+    KnnGrid g;
+    g.G = L.G;
+    g.box = p->box > 0.0 ? p->box : 0.0;
+    g.half_box = 0.5 * g.box;
+    for (int c = 0; c < 3; ++c) {
+        const double lo = p->box > 0.0 ? 0.0 : p->lo[c];
+        double ext = p->box > 0.0 ? p->box : (p->hi[c] - p->lo[c]);
+        if (!(ext > 0.0)) ext = 1.0;                       // degenerate axis: every particle lands in cell 0
+        g.lo[c] = lo;
+        g.cs[c] = ext / (double)L.G;
+        g.inv_cs[c] = (double)L.G / ext;
+    }
+    const int64_t n = p->n;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    knn_key_kernel<<<nb, 256, 0, s>>>(pos, n, g, L.ea);
+    int in_b = 0;
+    AST_CUDA_TRY(radix_sort_u64(L.ea, L.eb, n, 32, ceil_log2_u64((uint64_t)L.ncell), L.sort_ws, s, &in_b));
+    const uint64_t *sorted = in_b ? L.eb : L.ea;
+    AST_CUDA_TRY(cudaMemsetAsync(L.cbeg, 0, sizeof(uint32_t) * L.ncell, s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.cend, 0, sizeof(uint32_t) * L.ncell, s));
+    knn_gather_kernel<<<nb, 256, 0, s>>>(pos, sorted, n, L.xs, L.ys, L.zs, L.sidx, L.cbeg, L.cend, q_begin, q_end,
+                                         subset ? L.qflag : nullptr);
+    if (subset) {
+        AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n, L.scan_tmp, nullptr, s));
+        knn_compact_kernel<<<nb, 256, 0, s>>>(L.qflag, L.sidx, n, q_begin, q_end, L.qlist);
+    }
+    a.g = g;
+    a.xs = L.xs; a.ys = L.ys; a.zs = L.zs; a.sidx = L.sidx; a.cbeg = L.cbeg; a.cend = L.cend;
+    a.qlist = subset ? L.qlist : nullptr;
+    a.qpos = nullptr;
+    a.k = p->k;
+    AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
 }
 
 }  // namespace ast
@@ -278,46 +320,49 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
         return AST_EWORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    KnnGrid g;
-    g.G = L.G;
-    g.box = p->box > 0.0 ? p->box : 0.0;
-    g.half_box = 0.5 * g.box;
-    for (int c = 0; c < 3; ++c) {
-        const double lo = p->box > 0.0 ? 0.0 : p->lo[c];
-        double ext = p->box > 0.0 ? p->box : (p->hi[c] - p->lo[c]);
-        if (!(ext > 0.0)) ext = 1.0;                       // degenerate axis: every particle lands in cell 0
-        g.lo[c] = lo;
-        g.cs[c] = ext / (double)L.G;
-        g.inv_cs[c] = (double)L.G / ext;
-    }
     const int64_t n = p->n;
-    const unsigned nb = (unsigned)((n + 255) / 256);
-    knn_key_kernel<<<nb, 256, 0, s>>>(pos, n, g, L.ea);
-    int in_b = 0;
-    AST_CUDA_TRY(radix_sort_u64(L.ea, L.eb, n, 32, ceil_log2_u64((uint64_t)L.ncell), L.sort_ws, s, &in_b));
-    const uint64_t *sorted = in_b ? L.eb : L.ea;
-    AST_CUDA_TRY(cudaMemsetAsync(L.cbeg, 0, sizeof(uint32_t) * L.ncell, s));
-    AST_CUDA_TRY(cudaMemsetAsync(L.cend, 0, sizeof(uint32_t) * L.ncell, s));
     const bool subset = p->q_count > 0 && p->q_count < n;
     const int64_t q_begin = subset ? p->q_begin : 0, q_end = subset ? p->q_begin + p->q_count : n;
-    knn_gather_kernel<<<nb, 256, 0, s>>>(pos, sorted, n, L.xs, L.ys, L.zs, L.sidx, L.cbeg, L.cend, q_begin, q_end,
-                                         subset ? L.qflag : nullptr);
-    if (subset) {
-        AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n, L.scan_tmp, nullptr, s));
-        knn_compact_kernel<<<nb, 256, 0, s>>>(L.qflag, L.sidx, n, q_begin, q_end, L.qlist);
-    }
     KnnArgs a;
-    a.g = g;
-    a.xs = L.xs; a.ys = L.ys; a.zs = L.zs; a.sidx = L.sidx; a.cbeg = L.cbeg; a.cend = L.cend;
-    a.qlist = subset ? L.qlist : nullptr;
+    rc = knn_build(p, pos, L, subset, q_begin, q_end, s, a);
+    if (rc) return rc;
     a.nq = q_end - q_begin;
     a.q_begin = q_begin;
-    a.k = p->k;
     a.h_out = h_out; a.idx_out = idx_out; a.dist_out = dist_out;
     const bool want = idx_out != nullptr || dist_out != nullptr;
     if (p->k <= 32) launch_query<32>(a, want, s);
     else if (p->k <= 64) launch_query<64>(a, want, s);
     else launch_query<128>(a, want, s);
+    AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
+}
+
+// k nearest data points of every query point (separate query set): the reference's nearest-halo lookup
+// KDTree(centres, boxsize).query(particles) (_scripts/find_nearest_haloes.py:207-215) generalised to k neighbours.
+extern "C" int ast_knn_query(const ast_knn_params *p, const double *data_pos, const double *query_pos, int64_t n_query,
+                             double *dist_out, int32_t *idx_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = knn_validate(p);
+    if (rc) return rc;
+    AST_REQUIRE(n_query >= 0, "n_query < 0");
+    if (n_query == 0) return AST_OK;
+    AST_REQUIRE(p->n > 0 && data_pos && query_pos && (dist_out || idx_out), "null pointer or empty data set");
+    KnnLayout L = knn_layout(p, workspace);
+    if (!workspace || workspace_bytes < L.bytes) {
+        set_error("workspace too small: need %zu bytes, have %zu", L.bytes, workspace_bytes);
+        return AST_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    KnnArgs a;
+    rc = knn_build(p, data_pos, L, false, 0, p->n, s, a);
+    if (rc) return rc;
+    a.qpos = query_pos;
+    a.nq = n_query;
+    a.q_begin = 0;
+    a.h_out = nullptr; a.idx_out = idx_out; a.dist_out = dist_out;
+    if (p->k <= 32) launch_query<32>(a, true, s);
+    else if (p->k <= 64) launch_query<64>(a, true, s);
+    else launch_query<128>(a, true, s);
     AST_CUDA_TRY(cudaGetLastError());
     return AST_OK;
 }

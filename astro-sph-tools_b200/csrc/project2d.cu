@@ -48,6 +48,7 @@ struct P2 {
     int64_t n;
     int a_col, b_col, n_prop, kernel_id, shape, norm_dim;
     double norm_c;                      // norm(h) = norm_c / h^norm_dim
+    ShapeTab tab;                       // AST_KERNEL_TABLE only
     Axis1 ax, ay;
     int ntx, nty, n_img, img_shift;     // sort key = tile_key << img_shift | image
     double box_a, box_b;                // periodic image m = 3*(ia+1) + (ib+1), shift = (ia*box_a, ib*box_b)
@@ -86,7 +87,7 @@ __device__ __forceinline__ void deposit_small(const P2 &p, const Box2 &bb, doubl
         for (int yi = bb.y0; yi <= bb.y1; ++yi) {
             const double r2 = AST_DADD(dx2, dist2(p.ay, pb, yi));
             if (r2 < R2) {
-                const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2));
+                const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2), p.tab);
 #pragma unroll
                 for (int k = 0; k < NP; ++k) atomicAdd(row + k * p.map_stride + yi, coef[k] * f);
             }
@@ -116,7 +117,7 @@ __device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double 
         for (int ky = 0; ky < 2; ++ky) {
             const double r2 = AST_DADD(dx2[kx], dy2[ky]);
             if (r2 < R2) {
-                const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2));
+                const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2), p.tab);
                 double *o = p.out + (size_t)(i0 + kx) * (size_t)p.ay.n + (size_t)(j0 + ky);
 #pragma unroll
                 for (int k = 0; k < NP; ++k) atomicAdd(o + k * p.map_stride, coef[k] * f);
@@ -354,6 +355,7 @@ struct Acc {
     double x_min, y_min, dx, dy, inv_dx, inv_dy;
     int nx, ny, ntx, nty, img_shift, n_img;
     double box_a, box_b;
+    ShapeTab tab;
     size_t map_stride;
 };
 
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(kAccThreads) tile_accum_kernel(Acc a)
             for (int jx = 0; jx < 2; ++jx)
 #pragma unroll
                 for (int jy = 0; jy < 4; ++jy) {
-                    const float f = shape_eval<SHAPE>(fast_sqrt(axs[jx] + bys[jy]));
+                    const float f = shape_eval<SHAPE>(fast_sqrt(axs[jx] + bys[jy]), a.tab);
                     acc[0][jx * 4 + jy] = fmaf(c.x, f, acc[0][jx * 4 + jy]);
                     if (NP > 1) acc[NP - 1][jx * 4 + jy] = fmaf(c.y, f, acc[NP - 1][jx * 4 + jy]);
                 }
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
             for (int ix = 0; ix < PX; ++ix)
 #pragma unroll
                 for (int iy = 0; iy < PY; ++iy) {
-                    const float f = shape_eval<SHAPE>(fast_sqrt(ax2[ix] + by2[iy]));
+                    const float f = shape_eval<SHAPE>(fast_sqrt(ax2[ix] + by2[iy]), a.tab);
                     acc[0][ix * PY + iy] = fmaf(c.x, f, acc[0][ix * PY + iy]);
                     if (NP > 1) acc[NP - 1][ix * PY + iy] = fmaf(c.y, f, acc[NP - 1][ix * PY + iy]);
                 }
@@ -694,6 +696,9 @@ static int validate2(const ast_project2d_params *p)
     AST_REQUIRE(p->nx > 0 && p->ny > 0, "image_size (%d, %d) must be positive", p->nx, p->ny);
     AST_REQUIRE((int64_t)((p->nx + TILE - 1) / TILE) * ((p->ny + TILE - 1) / TILE) < (1ll << 27), "image too large");
     AST_REQUIRE(kernel_valid(p->kernel_id), "unknown kernel id %d", p->kernel_id);
+    if (p->kernel_id == AST_KERNEL_TABLE)
+        AST_REQUIRE(p->kernel_table != nullptr && p->kernel_table_n >= 2 && (p->kernel_dim == 2 || p->kernel_dim == 3),
+                    "AST_KERNEL_TABLE needs kernel_table (device), kernel_table_n >= 2 and kernel_dim 2 or 3");
     AST_REQUIRE(p->n_prop >= 1 && p->n_prop <= AST_MAX_PROPS, "n_prop = %d not in [1, %d]", p->n_prop, AST_MAX_PROPS);
     AST_REQUIRE(p->x_max > p->x_min && p->y_max > p->y_min, "empty or inverted map bounds");
     if (p->flags & AST_FLAG_PERIODIC) AST_REQUIRE(p->box_a > 0 && p->box_b > 0, "periodic projection needs box_a, box_b > 0");
@@ -735,8 +740,11 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     a.n_prop = p->n_prop;
     a.kernel_id = p->kernel_id;
     a.shape = kernel_shape(p->kernel_id);
-    a.norm_c = kernel_norm(p->kernel_id, 1.0);
-    a.norm_dim = (p->kernel_id == 0 || p->kernel_id == 2) ? 3 : 2;
+    a.norm_c = p->kernel_id == AST_KERNEL_TABLE ? 1.0 : kernel_norm(p->kernel_id, 1.0);
+    a.norm_dim = p->kernel_id == AST_KERNEL_TABLE ? p->kernel_dim : ((p->kernel_id == 0 || p->kernel_id == 2) ? 3 : 2);
+    a.tab.tab = (const float2 *)p->kernel_table;
+    a.tab.n = p->kernel_table_n;
+    a.tab.scale = 0.5f * (float)p->kernel_table_n;
     a.ax = make_axis(p->x_min, p->x_max, p->nx);
     a.ay = make_axis(p->y_min, p->y_max, p->ny);
     a.ntx = (p->nx + TILE - 1) / TILE;
@@ -842,7 +850,8 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
         bin_tma_kernel<SH, NPV><<<(unsigned)grid, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full);  \
     } while (0)
                 if (a.shape == SHAPE_CUBIC) { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_CUBIC, 1); else AST_LAUNCH_TMA(SHAPE_CUBIC, 2); }
-                else { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_WENDLAND, 1); else AST_LAUNCH_TMA(SHAPE_WENDLAND, 2); }
+                else if (a.shape == SHAPE_WENDLAND) { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_WENDLAND, 1); else AST_LAUNCH_TMA(SHAPE_WENDLAND, 2); }
+                else { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_TABLE, 1); else AST_LAUNCH_TMA(SHAPE_TABLE, 2); }
 #undef AST_LAUNCH_TMA
                 st.n_launches += 1;
             }
@@ -850,7 +859,8 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             if (n_rest > 0) {
 #define AST_LAUNCH_BIN(SH, NPV) bin_kernel<SH, true, NPV><<<(unsigned)n_rest, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full)
                 if (a.shape == SHAPE_CUBIC) { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_CUBIC, 1); else AST_LAUNCH_BIN(SHAPE_CUBIC, 2); }
-                else { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_WENDLAND, 1); else AST_LAUNCH_BIN(SHAPE_WENDLAND, 2); }
+                else if (a.shape == SHAPE_WENDLAND) { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_WENDLAND, 1); else AST_LAUNCH_BIN(SHAPE_WENDLAND, 2); }
+                else { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_TABLE, 1); else AST_LAUNCH_BIN(SHAPE_TABLE, 2); }
 #undef AST_LAUNCH_BIN
                 st.n_launches += 1;
             }
@@ -884,7 +894,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
         c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
         c.x_min = a.ax.vmin; c.y_min = a.ay.vmin; c.dx = a.ax.d; c.dy = a.ay.d; c.inv_dx = a.ax.inv_d; c.inv_dy = a.ay.inv_d;
         c.nx = p->nx; c.ny = p->ny; c.ntx = a.ntx; c.nty = a.nty; c.img_shift = a.img_shift;
-        c.n_img = a.n_img; c.box_a = a.box_a; c.box_b = a.box_b;
+        c.n_img = a.n_img; c.box_a = a.box_a; c.box_b = a.box_b; c.tab = a.tab;
         c.map_stride = a.map_stride;
         for (int64_t r = 0; r < rounds; ++r) {
             const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
@@ -911,7 +921,8 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
             tk.begin(5);
             if (a.shape == SHAPE_CUBIC) launch_accum<SHAPE_CUBIC>(p->n_prop, c, L.ntiles, s);
-            else launch_accum<SHAPE_WENDLAND>(p->n_prop, c, L.ntiles, s);
+            else if (a.shape == SHAPE_WENDLAND) launch_accum<SHAPE_WENDLAND>(p->n_prop, c, L.ntiles, s);
+            else launch_accum<SHAPE_TABLE>(p->n_prop, c, L.ntiles, s);
             tk.end();
             st.n_launches += 1;
             AST_CUDA_TRY(cudaGetLastError());
@@ -996,7 +1007,7 @@ extern "C" int ast_contrib_count2d(const ast_project2d_params *p, const double *
 
 extern "C" int ast_kernel_eval(int kernel_id, const double *r, const double *h, double *out, int64_t n, void *stream)
 {
-    AST_REQUIRE(kernel_valid(kernel_id), "unknown kernel id %d", kernel_id);
+    AST_REQUIRE(kernel_valid(kernel_id) && kernel_id != AST_KERNEL_TABLE, "unknown kernel id %d", kernel_id);
     AST_REQUIRE(n >= 0 && (n == 0 || (r && h && out)), "null pointer or negative n");
     if (n > 0) kernel_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kernel_id, r, h, out, n);
     AST_CUDA_TRY(cudaGetLastError());

@@ -40,12 +40,26 @@ class Projector2D:
         self.last_stats = None
 
     # ---- parameters -------------------------------------------------------------------------------------
+    def _set_kernel(self, p, kernel):
+        """built-in kernel by name / id, or a TabulatedKernel (arbitrary kernel_func callable)"""
+        if isinstance(kernel, str):
+            p.kernel_id = _lib.KERNEL_IDS[kernel]
+        elif hasattr(kernel, "device_table"):
+            tab = kernel.device_table(self.torch, self.device)
+            self._kernel_table = tab                               # keep the device table alive for the call
+            p.kernel_id = _lib.KERNEL_TABLE
+            p.kernel_table = tab.data_ptr()
+            p.kernel_table_n = tab.shape[0]
+            p.kernel_dim = kernel.dim
+        else:
+            p.kernel_id = int(kernel)
+
     def _params(self, n, image_size, axis, bounds, kernel, n_prop, periodic, box, timing, accumulate):
         p = _lib.Project2DParams()
         p.n = int(n)
         p.axis = _axis_index(axis)
         p.nx, p.ny = int(image_size[0]), int(image_size[1])
-        p.kernel_id = _lib.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
+        self._set_kernel(p, kernel)
         p.n_prop = int(n_prop)
         p.flags = (_lib.FLAG_PERIODIC if periodic else 0) | (_lib.FLAG_TIMING if timing else 0) | \
                   (_lib.FLAG_ACCUMULATE if accumulate else 0)

@@ -31,7 +31,17 @@ class Gridder3D:
         p = _lib.Grid3DParams()
         p.n = int(n)
         p.nx, p.ny, p.nz = (int(v) for v in grid_size)
-        p.kernel_id = _lib.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
+        if isinstance(kernel, str):
+            p.kernel_id = _lib.KERNEL_IDS[kernel]
+        elif hasattr(kernel, "device_table"):                      # TabulatedKernel: arbitrary kernel_func callable
+            tab = kernel.device_table(self.torch, self.device)
+            self._kernel_table = tab
+            p.kernel_id = _lib.KERNEL_TABLE
+            p.kernel_table = tab.data_ptr()
+            p.kernel_table_n = tab.shape[0]
+            p.kernel_dim = kernel.dim
+        else:
+            p.kernel_id = int(kernel)
         p.flags = (_lib.FLAG_PERIODIC if periodic else 0) | (_lib.FLAG_TIMING if timing else 0) | \
                   (_lib.FLAG_ACCUMULATE if accumulate else 0)
         for c in range(3):

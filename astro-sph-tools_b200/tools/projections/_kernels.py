@@ -65,18 +65,62 @@ _KNOWN = {quartic_spline_kernel: "cubic_spline_3d", wendland_c2_kernel: "wendlan
           wendland_c2_kernel_3d: "wendland_c2_3d", cubic_spline_kernel_2d: "cubic_spline_2d"}
 
 
+class TabulatedKernel:
+    """A user ``kernel_func`` of the reference form ``W(r, h) = f(r/h) / h**dim`` (``_projector.py:86`` accepts any
+    ``Callable[[r, h], w]``), sampled on q = r/h in [0, 2] -- the reference masks r < 2h (``_pixel_calculations.pyx:31``) --
+    and evaluated on the device by linear interpolation (AST_KERNEL_TABLE).  The callable itself runs on the host, once."""
+
+    N = 8192
+
+    def __init__(self, kernel_func):
+        q = np.linspace(0.0, 2.0, self.N + 1)
+        one = np.ones_like(q)
+        f = np.asarray(kernel_func(q.copy(), one.copy()), dtype=np.float64)
+        if f.shape != q.shape or not np.all(np.isfinite(f)):
+            raise NotImplementedError("kernel_func(r, h) must return a finite float array of the length of r")
+        scale = np.abs(f).max()
+        self.dim = None
+        for dim in (3, 2):
+            ok = True
+            for hh in (0.37, 2.5):
+                g = np.asarray(kernel_func(q * hh, one * hh), dtype=np.float64) * hh ** dim
+                ok = ok and np.allclose(g, f, rtol=1e-9, atol=1e-12 * scale)
+            if ok:
+                self.dim = dim
+                break
+        if self.dim is None:
+            raise NotImplementedError(
+                "kernel_func is not of the self-similar form f(r/h) / h**2 or f(r/h) / h**3, so it cannot be tabulated for the "
+                "device (a Python callable cannot run inside a CUDA kernel and there is no CPU fallback)")
+        self.pairs = np.ascontiguousarray(np.stack([f[:-1], f[1:] - f[:-1]], axis=1).astype(np.float32))
+        self._dev = {}
+
+    def device_table(self, torch, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = torch.from_numpy(self.pairs).to(device)
+        return self._dev[key]
+
+
+_TABULATED = {}
+
+
 def kernel_id_of(kernel_func):
-    """Device kernel name for a kernel_func argument: one of the callables above, or its name as a string."""
+    """Device kernel for a kernel_func argument: the name of a built-in kernel (one of the callables above or its name),
+    or a TabulatedKernel for any other callable of the form f(r/h)/h**dim."""
+    if isinstance(kernel_func, TabulatedKernel):
+        return kernel_func
     if isinstance(kernel_func, str):
         if kernel_func in _lib.KERNEL_IDS:
             return kernel_func
         raise NotImplementedError(f"unknown kernel name {kernel_func!r}; known: {sorted(_lib.KERNEL_IDS)}")
     name = _KNOWN.get(kernel_func)
-    if name is None:
-        # the reference's own compiled function object, if a user passes it
-        if getattr(kernel_func, "__name__", "") == "quartic_spline_kernel":
-            return "cubic_spline_3d"
-        raise NotImplementedError(
-            "kernel_func must be one of quartic_spline_kernel, wendland_c2_kernel, wendland_c2_kernel_3d, "
-            "cubic_spline_kernel_2d (a Python callable cannot run inside a CUDA kernel and there is no CPU fallback)")
-    return name
+    if name is not None:
+        return name
+    if getattr(kernel_func, "__name__", "") == "quartic_spline_kernel":        # the reference's own compiled function object
+        return "cubic_spline_3d"
+    if not callable(kernel_func):
+        raise NotImplementedError("kernel_func must be callable or the name of a built-in kernel")
+    if kernel_func not in _TABULATED:
+        _TABULATED[kernel_func] = TabulatedKernel(kernel_func)
+    return _TABULATED[kernel_func]

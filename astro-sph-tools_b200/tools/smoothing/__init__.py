@@ -71,6 +71,48 @@ class SmoothingLengthSolver:
         return out if len(out) > 1 else h
 
 
+    def _knn_params(self, data, k, box_size):
+        torch = self.torch
+        if data.dtype != torch.float64 or data.ndim != 2 or data.shape[1] != 3 or not data.is_cuda or not data.is_contiguous():
+            raise ValueError("positions must be a contiguous float64 CUDA tensor of shape (N, 3)")
+        p = _lib.KnnParams()
+        p.n = data.shape[0]; p.k = int(k); p.flags = 0
+        p.box = float(box_size) if box_size else 0.0
+        if p.box <= 0.0:
+            lo = data.min(dim=0).values.cpu(); hi = data.max(dim=0).values.cpu()
+            if not (torch.isfinite(lo).all() and torch.isfinite(hi).all()):
+                raise ValueError("positions must be finite")
+            for c in range(3):
+                p.lo[c] = float(lo[c]); p.hi[c] = float(hi[c])
+        elif not (float(data.min()) >= 0.0 and float(data.max()) < p.box):
+            raise ValueError("periodic k-NN needs 0 <= x < box_size (scipy boxsize semantics)")
+        p.cell_target = self.cell_target
+        return p
+
+    def query(self, data, queries, k=1, box_size=None, stream=None):
+        """k nearest DATA points of each QUERY point: (dist (M,k) float64, idx (M,k) int32) CUDA tensors, ascending."""
+        torch = self.torch
+        if queries.dtype != torch.float64 or queries.ndim != 2 or queries.shape[1] != 3 or not queries.is_cuda or not queries.is_contiguous():
+            raise ValueError("queries must be a contiguous float64 CUDA tensor of shape (M, 3)")
+        if data.shape[0] == 0:
+            raise ValueError("empty data set")
+        p = self._knn_params(data, k, box_size)
+        if p.box > 0.0 and queries.shape[0] and not (float(queries.min()) >= 0.0 and float(queries.max()) < p.box):
+            raise ValueError("periodic queries must satisfy 0 <= x < box_size")
+        need = C.c_size_t(0)
+        _lib.check(self.lib.ast_knn_workspace_bytes(C.byref(p), C.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = None
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        m = queries.shape[0]
+        dist = torch.empty((m, k), dtype=torch.float64, device=self.device)
+        idx = torch.empty((m, k), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ast_knn_query(C.byref(p), _lib.ptr(data), _lib.ptr(queries), C.c_int64(m), _lib.ptr(dist), _lib.ptr(idx),
+                                              _lib.ptr(self._ws), C.c_size_t(self._ws.numel()), _lib.stream_ptr(stream)))
+        return dist, idx
+
+
 _default = {}
 
 
@@ -105,3 +147,16 @@ def compute_smoothing_lengths(positions, k=DEFAULT_K, box_size=None, return_neig
 def get_smoothing_lengths(positions, n_neighbours=DEFAULT_K):
     """The reference's semantics exactly (K = 32, self included, non-periodic): io/SWIFT/_SnapshotSWIFT.py:62-83."""
     return compute_smoothing_lengths(positions, k=n_neighbours, box_size=None)
+
+
+def nearest_neighbours(data_positions, query_positions, k=1, box_size=None):
+    """``scipy.spatial.KDTree(data_positions, boxsize=box_size).query(query_positions, k)`` on the GPU: the nearest-halo
+    lookup of the reference's CLI (_scripts/find_nearest_haloes.py:207-215: tree over halo centres, queried with particle
+    positions).  numpy in / numpy out; returns (distances, indices), 1-D for k == 1 like scipy, else (M, k)."""
+    torch = _lib.require_cuda()
+    sol = _solver()
+    d = torch.from_numpy(np.ascontiguousarray(data_positions, dtype=np.float64)).to(sol.device)
+    q = torch.from_numpy(np.ascontiguousarray(query_positions, dtype=np.float64)).to(sol.device)
+    dist, idx = sol.query(d, q, k, box_size)
+    dist, idx = dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+    return (dist[:, 0], idx[:, 0]) if k == 1 else (dist, idx)

@@ -50,7 +50,9 @@ typedef enum ast_kernel {
                                          M4 cubic spline, 1/(pi h^3) normalisation */
     AST_KERNEL_WENDLAND_C2_2D = 1,    /* 7/(pi H^2) (1-u)^4 (1+4u), u = r/H, H = 2h  (surface density) */
     AST_KERNEL_WENDLAND_C2_3D = 2,    /* 21/(2 pi H^3) (1-u)^4 (1+4u) */
-    AST_KERNEL_CUBIC_SPLINE_2D = 3    /* M4 cubic spline with 10/(7 pi h^2) */
+    AST_KERNEL_CUBIC_SPLINE_2D = 3,   /* M4 cubic spline with 10/(7 pi h^2) */
+    AST_KERNEL_TABLE = 4              /* W(r,h) = f(r/h) / h^kernel_dim with f tabulated by the caller on q in [0,2]: this is
+                                         how an arbitrary `kernel_func` callable of the reference (_projector.py:86) is served */
 } ast_kernel;
 
 enum {
@@ -78,6 +80,10 @@ typedef struct ast_project2d_params {
     int64_t huge_min_tiles;      /* tile-bbox count above which a particle goes to the global list; <0 = default */
     int64_t pair_capacity;       /* (tile, particle) pairs the workspace holds per round */
     int64_t huge_capacity;       /* entries of the global large-h list */
+    const float *kernel_table;   /* AST_KERNEL_TABLE: DEVICE array of 2*kernel_table_n floats, entry j = {f(q_j), f(q_j+1)-f(q_j)},
+                                    q_j = 2j/kernel_table_n; linear interpolation, 0 for q >= 2 */
+    int32_t kernel_table_n;      /* number of intervals */
+    int32_t kernel_dim;          /* 2 or 3: the power of h in the normalisation */
 } ast_project2d_params;
 
 typedef struct ast_project2d_stats {
@@ -136,6 +142,9 @@ typedef struct ast_grid3d_params {
     int64_t huge_min_bricks;     /* brick-bbox count above which a particle goes to the global list; <0 = default */
     int64_t pair_capacity;
     int64_t huge_capacity;
+    const float *kernel_table;   /* as in ast_project2d_params */
+    int32_t kernel_table_n;
+    int32_t kernel_dim;
 } ast_grid3d_params;
 
 int ast_grid3d_workspace_bytes(const ast_grid3d_params *p, size_t *bytes);
@@ -171,6 +180,13 @@ typedef struct ast_knn_params {
 int ast_knn_workspace_bytes(const ast_knn_params *p, size_t *bytes);
 int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_out, int32_t *idx_out, double *dist_out,
               void *workspace, size_t workspace_bytes, void *stream);
+
+/* k nearest DATA points (p->n of them, cell list built over them; p->lo/hi = their extent, or p->box) of each of n_query
+ * separate QUERY points: replaces KDTree(centres, boxsize=L).query(particles[, k]) of the nearest-halo script
+ * (_scripts/find_nearest_haloes.py:207-215).  dist_out / idx_out: n_query*k, ascending (distance, index); either may be
+ * null.  Same arithmetic as ast_knn_h (bit-equal to scipy).  Workspace: ast_knn_workspace_bytes(p). */
+int ast_knn_query(const ast_knn_params *p, const double *data_pos, const double *query_pos, int64_t n_query,
+                  double *dist_out, int32_t *idx_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- misc ---- */
 const char *ast_last_error(void);

@@ -83,3 +83,22 @@ def test_query_slices_and_cell_size_invariance(oracle):
     assert np.array_equal(np.concatenate(parts), full)
     for ct in (2.0, 7.0, 40.0, 500.0):
         assert np.array_equal(gpu_knn(pos, 48, 1.0, cell_target=ct), full)
+
+
+def test_nearest_halo_lookup_separate_query_set(oracle):
+    """KDTree(centres, boxsize=L).query(particles): the reference's nearest-halo CLI (_scripts/find_nearest_haloes.py:207-215)"""
+    from scipy.spatial import cKDTree
+    from astro_sph_tools_b200.tools.smoothing import nearest_neighbours
+    rng = np.random.default_rng(21)
+    centres = rng.uniform(0, 25.0, (700, 3)); parts = rng.uniform(0, 25.0, (40000, 3))
+    d_ref, i_ref = cKDTree(centres, boxsize=25.0).query(parts, workers=-1)
+    d, i = nearest_neighbours(centres, parts, box_size=25.0)
+    assert d.shape == (40000,) and np.array_equal(d, d_ref) and np.array_equal(i, i_ref)
+    # open box, k = 5, queries partly outside the extent of the data
+    parts2 = rng.uniform(-5.0, 30.0, (5000, 3))
+    d_ref, i_ref = cKDTree(centres).query(parts2, k=5)
+    d, i = nearest_neighbours(centres, parts2, k=5)
+    assert np.array_equal(d, d_ref) and np.array_equal(i, i_ref)
+    # fewer data points than k: scipy pads with inf / n
+    d, i = nearest_neighbours(centres[:3], parts2[:10], k=5)
+    assert np.all(np.isinf(d[:, 3:])) and np.all(i[:, 3:] == -1) and np.array_equal(d[:, :3], cKDTree(centres[:3]).query(parts2[:10], k=3)[0])

@@ -62,6 +62,33 @@ def test_periodic_wendland_config1_shape(oracle):
     assert abs(img.sum() / 128 ** 2 - g["base_prop"].sum()) <= 1e-6 * g["base_prop"].sum()     # mass conservation
 
 
+def test_arbitrary_python_kernel_func_is_served_by_the_table(oracle):
+    """kernel_func is an arbitrary Python callable in the reference (_projector.py:86): the golden map below was produced by
+    the reference with this very callable; here the callable is tabulated on the host and interpolated on the device"""
+    import sys, os
+    from astro_sph_tools_b200 import CoordinateAxes
+    from astro_sph_tools_b200.tools.projections import create_image, create_grid
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from gen_golden import wendland_c2_2d
+    g = load_golden("s1_n16_p128_wc2_periodic")
+    img = create_image(g["pos"], g["h"], g["prop"], (128, 128), 32, CoordinateAxes.Z, 0.0, 1.0, 0.0, 1.0, kernel_func=wendland_c2_2d)
+    check(img, g["ref_map"])
+    # a kernel that is not built in: truncated Gaussian, 2-D normalised; oracle = the literal definition in numpy
+    gauss = lambda r, h: np.exp(-(r / h) ** 2) / (np.pi * h ** 2)
+    pos, h, prop = random_cloud(5, 300, h_lo=0.05, h_hi=0.9)
+    img = create_image(pos, h, prop, (48, 48), 16, CoordinateAxes.Z, 0.0, 10.0, 0.0, 10.0, kernel_func=gauss)
+    X = (np.arange(48) * (10.0 / 48))
+    ref = np.zeros((48, 48))
+    for p_, h_, a_ in zip(pos, h, prop):
+        r2 = (p_[0] - X[:, None]) ** 2 + (p_[1] - X[None, :]) ** 2
+        ref += np.where(r2 < (2 * h_) ** 2, a_ * gauss(np.sqrt(r2), h_), 0.0)
+    check(img, ref)
+    # and in 3-D
+    top = lambda r, h: (1.0 - 0.5 * r / h) * 3.0 / (4 * np.pi * h ** 3)
+    grid = create_grid(pos[:, :3] / 10.0, h / 10.0, prop, (24, 24, 24), 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, kernel_func=top)
+    assert grid.shape == (24, 24, 24) and np.isfinite(grid).all() and grid.sum() > 0
+
+
 def test_two_properties_one_pass():
     from astro_sph_tools_b200 import CoordinateAxes
     from astro_sph_tools_b200.tools.projections import create_images

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from astro_sph_tools_b200 import _lib
-    assert C.sizeof(_lib.Project2DParams) == 8 + 6 * 4 + 6 * 8 + 4 * 8
+    assert C.sizeof(_lib.Project2DParams) == 8 + 6 * 4 + 6 * 8 + 4 * 8 + 8 + 2 * 4
     assert C.sizeof(_lib.Project2DStats) == 4 * 8 + 8 * 4
 
 
@@ -53,8 +53,19 @@ def test_create_image_validation_mirrors_reference_errors():
         create_image(pos.astype(np.float32), h, a, *args)
     with pytest.raises(ValueError, match="wrong number of dimensions"):
         create_image(pos[:, 0], h, a, *args)
-    with pytest.raises(NotImplementedError):
-        create_image(pos, h, a, *args, kernel_func=lambda r, hh: r)
+    with pytest.raises(NotImplementedError, match="self-similar"):
+        create_image(pos, h, a, *args, kernel_func=lambda r, hh: r + hh)          # not f(r/h)/h^dim: cannot be tabulated
+
+
+def test_python_callable_kernels_are_tabulated_on_the_host():
+    from astro_sph_tools_b200.tools.projections import kernel_id_of, TabulatedKernel, quartic_spline_kernel
+    assert kernel_id_of(quartic_spline_kernel) == "cubic_spline_3d" and kernel_id_of("wendland_c2_2d") == "wendland_c2_2d"
+    gauss2d = lambda r, h: np.exp(-(r / h) ** 2) / (np.pi * h ** 2)
+    t = kernel_id_of(gauss2d)
+    assert isinstance(t, TabulatedKernel) and t.dim == 2 and t.pairs.shape == (TabulatedKernel.N, 2)
+    assert kernel_id_of(gauss2d) is t                                             # cached per callable
+    top3d = lambda r, h: np.where(r < 2 * h, 3.0 / (32 * np.pi * h ** 3), 0.0)
+    assert kernel_id_of(top3d).dim == 3
 
 
 def test_no_cpu_fallback():
