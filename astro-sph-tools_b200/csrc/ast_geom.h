@@ -88,6 +88,13 @@ AST_HD bool range1(const Axis1 &a, double p, double h, double R2, int &lo, int &
     return true;
 }
 
+// Cheap conservative pre-test used to skip periodic images: false only when no sample of the axis can lie within 2h of p
+// (one sample spacing of slack against rounding), i.e. only when range1 would return false anyway.  NaN -> false.
+AST_HD bool may_touch(const Axis1 &a, double p, double h2)
+{
+    return (p + h2 >= a.vmin - a.d) && (p - h2 <= a.vmin + ((double)a.n) * a.d);
+}
+
 // index of the sample at or just below p (seed only; callers look at e-1, e, e+1)
 AST_HD int floor_index(const Axis1 &a, double p, int lo, int hi)
 {
@@ -95,21 +102,19 @@ AST_HD int floor_index(const Axis1 &a, double p, int lo, int hi)
     return t < (double)lo ? lo : (t > (double)hi ? hi : (int)t);
 }
 
-// min over i in [lo,hi] of dist2(p,i): attained at an end point or next to the particle (unimodality)
+// min over i in [lo,hi] of dist2(p,i).  |p - X(i)| is unimodal in i with its minimum at m* in {f, f+1}, f the true floor
+// of (p - vmin)/d; the seed e (computed with a multiply) satisfies |e - m*| <= 1.  Hence: e < lo -> the minimum over the
+// interval is at lo; e > hi -> at hi; otherwise among e-1, e, e+1 (clamped).  One or three evaluations, same value as
+// scanning the whole interval (oracle: brute force).
 AST_HD double min_dist2(const Axis1 &a, double p, int lo, int hi)
 {
-    int e = floor_index(a, p, lo, hi);
+    const double t = floor(AST_DMUL(AST_DSUB(p, a.vmin), a.inv_d));
+    if (t < (double)lo) return dist2(a, p, lo);
+    if (t > (double)hi) return dist2(a, p, hi);
+    const int e = (int)t;
     double m = dist2(a, p, e);
-    int c = e - 1 < lo ? lo : e - 1;
-    double v = dist2(a, p, c);
-    m = v < m ? v : m;
-    c = e + 1 > hi ? hi : e + 1;
-    v = dist2(a, p, c);
-    m = v < m ? v : m;
-    v = dist2(a, p, lo);
-    m = v < m ? v : m;
-    v = dist2(a, p, hi);
-    m = v < m ? v : m;
+    if (e > lo) { const double v = dist2(a, p, e - 1); m = v < m ? v : m; }
+    if (e < hi) { const double v = dist2(a, p, e + 1); m = v < m ? v : m; }
     return m;
 }
 

@@ -85,10 +85,11 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
     uint32_t npairs = 0, nhuge = 0;
     if (i < p.n) {
         const double x0[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
-        const double h = p.h[i], R2 = radius2(h);
+        const double h = p.h[i], R2 = radius2(h), h2 = 2.0 * h;
         bool need_rec = false;
         for (int m = 0; m < p.n_img; ++m) {
             const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
+            if (!may_touch(p.ax[0], q[0], h2) || !may_touch(p.ax[1], q[1], h2) || !may_touch(p.ax[2], q[2], h2)) continue;
             Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
             if (b.cls == CLS_SMALL) {
                 if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * norm3(p, h));
@@ -128,14 +129,16 @@ __global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_
     const bool any_huge = write_huge && hnext > hbase;
     if (!any_pairs && !any_huge) return;
     const int64_t i = (int64_t)blockIdx.x * kBin3Threads + threadIdx.x;
-    double x0[3] = { 0, 0, 0 }, h = 0, R2 = 0;
+    double x0[3] = { 0, 0, 0 }, h = 0, R2 = 0, h2 = 0;
     uint32_t npairs = 0, nhuge = 0;
     if (i < p.n) {
         x0[0] = p.pos[3 * i]; x0[1] = p.pos[3 * i + 1]; x0[2] = p.pos[3 * i + 2];
         h = p.h[i];
         R2 = radius2(h);
+        h2 = 2.0 * h;
         for (int m = 0; m < p.n_img; ++m) {
             const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
+            if (!may_touch(p.ax[0], q[0], h2) || !may_touch(p.ax[1], q[1], h2) || !may_touch(p.ax[2], q[2], h2)) continue;
             Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
             if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
             else if (b.cls == CLS_HUGE) ++nhuge;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_
     if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
     for (int m = 0; m < p.n_img; ++m) {
         const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
+        if (!may_touch(p.ax[0], q[0], h2) || !may_touch(p.ax[1], q[1], h2) || !may_touch(p.ax[2], q[2], h2)) continue;
         Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
         if (b.cls == CLS_TILED) {
             for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [&](uint32_t key) {

@@ -153,6 +153,7 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
     bool need_rec = false;
     for (int m = 0; m < p.n_img; ++m) {
         const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
+        if (!may_touch(p.ax, pa, AST_DMUL(2.0, h)) || !may_touch(p.ay, pb, AST_DMUL(2.0, h))) continue;   // image cannot reach the map
         Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
         if (b.cls == CLS_SMALL) {
             if (DEPOSIT) deposit_small<SHAPE, NP>(p, b.bb, pa, pb, R2, inv_h2, coef);
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
         R2 = radius2(h);
         for (int m = 0; m < p.n_img; ++m) {
             const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
+            if (!may_touch(p.ax, pa, AST_DMUL(2.0, h)) || !may_touch(p.ay, pb, AST_DMUL(2.0, h))) continue;   // image cannot reach the map
             Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
             if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
             else if (b.cls == CLS_HUGE) ++nhuge;
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
     if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
     for (int m = 0; m < p.n_img; ++m) {
         const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
+        if (!may_touch(p.ax, pa, AST_DMUL(2.0, h)) || !may_touch(p.ay, pb, AST_DMUL(2.0, h))) continue;   // image cannot reach the map
         Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
         if (b.cls == CLS_TILED) {
             for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [&](uint32_t key) {
