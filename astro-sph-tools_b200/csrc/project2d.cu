@@ -5,19 +5,20 @@
 // The reference gathers: for every pixel it scans every candidate particle.  Here the work is turned
 // round (scatter by particle, gather by screen tile):
 //
-//   K1 bin_kernel        one thread per particle: float64 bbox (ast_geom.h), class, pair count; particles whose
+//   K1 bin_tma_kernel    persistent CTAs, inputs staged through shared memory by the TMA engine (cp.async.bulk + mbarrier);
+//      (+ bin_kernel)    one thread per particle: float64 bbox (ast_geom.h), class, pair count; particles whose
 //                        bbox is a few pixels are deposited right here with float64 atomics (the HBM-bound
 //                        regime: inputs are read exactly once); the others get a 32-byte record.
 //   scan                 exclusive scan of the per-block pair counts.
 //   K3 emit_kernel       writes (tile key << 32 | particle) pairs in emit order.
 //   radix sort           stable, by tile key (scan_sort.cuh).
 //   K5 tile_range_kernel first/last pair of every tile.
-//   K6 tile_accum_kernel one CTA per 32x32-pixel tile, 4 warps each owning a 16x16 sub-tile, 8 pixels per
-//                        thread in registers; particle records are staged through shared memory in
-//                        tile-relative float32 (converted from float64 at staging time); per staged chunk the
-//                        float32 partial sums are folded into float64 accumulators; the tile is written once.
-//                        Particles covering more than huge_min_tiles tiles are not binned: every tile walks the
-//                        (short) global list of them and culls per warp.
+//   K6 subtile_accum_kernel  one CTA per 32x32-pixel tile, 8 autonomous warps each owning an 8x16 sub-tile, 2x2 pixels
+//                        per thread in registers; every warp stages 32 list entries at a time through its own
+//                        shared-memory slots in tile-relative float32 (converted from float64 at staging time), culls
+//                        them against its sub-tile and evaluates the hits; float32 partial sums are folded into
+//                        float64 accumulators; the tile is written once.  Particles covering more than huge_min_tiles
+//                        tiles are not binned: every tile walks the (short) global list of them and culls per warp.
 #include <string.h>
 
 #include "ast_geom.h"
@@ -30,8 +31,6 @@ namespace ast {
 
 constexpr int TILE = AST_TILE;
 constexpr int kBinThreads = 256;
-constexpr int kAccThreads = 128;
-constexpr int kChunk = 128;            // list entries staged per pass
 
 struct __align__(32) Rec {
     double pa, pb;             // in-plane position, float64 (tile-relative float32 is derived at staging time)
@@ -104,12 +103,16 @@ __device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double 
 {
     const double tx = AST_DMUL(AST_DSUB(pa, p.ax.vmin), p.ax.inv_d), ty = AST_DMUL(AST_DSUB(pb, p.ay.vmin), p.ay.inv_d);
     if (!(tx > -2.0 && tx < (double)p.ax.n + 1.0 && ty > -2.0 && ty < (double)p.ay.n + 1.0)) return;   // also NaN / inf
-    const int i0 = (int)floor(tx), j0 = (int)floor(ty);
+    // floor() already is the sample index as a double: X(i) = vmin + i*d needs no int -> double conversion
+    const double fx = floor(tx), fy = floor(ty);
+    const int i0 = (int)fx, j0 = (int)fy;
     double dx2[2], dy2[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        dx2[k] = (i0 + k >= 0 && i0 + k < p.ax.n) ? dist2(p.ax, pa, i0 + k) : INFINITY;
-        dy2[k] = (j0 + k >= 0 && j0 + k < p.ay.n) ? dist2(p.ay, pb, j0 + k) : INFINITY;
+        const double tx_k = AST_DSUB(pa, AST_DADD(p.ax.vmin, AST_DMUL(fx + (double)k, p.ax.d)));
+        const double ty_k = AST_DSUB(pb, AST_DADD(p.ay.vmin, AST_DMUL(fy + (double)k, p.ay.d)));
+        dx2[k] = (i0 + k >= 0 && i0 + k < p.ax.n) ? AST_DMUL(tx_k, tx_k) : INFINITY;
+        dy2[k] = (j0 + k >= 0 && j0 + k < p.ay.n) ? AST_DMUL(ty_k, ty_k) : INFINITY;
     }
 #pragma unroll
     for (int kx = 0; kx < 2; ++kx)
@@ -362,133 +365,7 @@ struct Acc {
     size_t map_stride;
 };
 
-template <int SHAPE, int NP>
-__global__ void __launch_bounds__(kAccThreads) tile_accum_kernel(Acc a)
-{
-    __shared__ float4 sP[kChunk];       // {ux*sx, uy*sy, sx, sy}  tile-relative, in units of h
-    __shared__ float4 sC[kChunk];       // {c0, c1, warp mask, -}
-    __shared__ int s_cnt[4];
-
-    const int tile = blockIdx.x;
-    const uint32_t beg = a.tbeg[tile], cnt = a.tend[tile] - beg;
-    const uint32_t total = cnt + a.n_huge;
-    if (total == 0) return;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = tile / a.nty, ty = tile - tx * a.nty;
-    const int X0 = tx * TILE, Y0 = ty * TILE;
-    // this thread's pixels: 2 (x) by 4 (y) inside the warp's 16x16 sub-tile
-    const int xl = 16 * (warp >> 1) + 2 * (lane >> 2);
-    const int yl = 16 * (warp & 1) + 4 * (lane & 3);
-    const float xf0 = (float)xl, xf1 = (float)(xl + 1);
-    const float yf0 = (float)yl, yf1 = (float)(yl + 1), yf2 = (float)(yl + 2), yf3 = (float)(yl + 3);
-
-    float acc[NP][8];
-    double acc64[NP][8];
-#pragma unroll
-    for (int k = 0; k < NP; ++k)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
-
-    const double ox = (double)X0, oy = (double)Y0;
-
-    for (uint32_t base = 0; base < total; base += kChunk) {
-        // ---- stage up to kChunk list entries: float64 record -> tile-relative float32, per-warp cull mask
-        const uint32_t j = base + tid;
-        float4 P = make_float4(0.f, 0.f, 0.f, 0.f), C = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t mask = 0;
-        if (j < total) {
-            uint32_t idx, m;
-            if (j < cnt) {
-                const uint64_t e = a.sorted[beg + j];
-                idx = (uint32_t)e;
-                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
-            } else {
-                const uint64_t e = a.huge[j - cnt];
-                idx = (uint32_t)e;
-                m = (uint32_t)(e >> 32);
-            }
-            const Rec r = a.rec[idx];
-            const double ux = (r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox;
-            const double uy = (r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy;
-            const float sx = (float)a.dx * r.inv_h, sy = (float)a.dy * r.inv_h;
-            const float fx = (float)ux, fy = (float)uy;
-            P = make_float4(fx * sx, fy * sy, sx, sy);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float lox = 16.f * (float)(w >> 1), loy = 16.f * (float)(w & 1);
-                const float ddx = fmaxf(fmaxf(lox - fx, fx - (lox + 15.f)), 0.f) * sx;
-                const float ddy = fmaxf(fmaxf(loy - fy, fy - (loy + 15.f)), 0.f) * sy;
-                if (ddx * ddx + ddy * ddy < 4.0001f) mask |= 1u << w;
-            }
-            C = make_float4(r.c[0], NP > 1 ? r.c[1] : 0.f, __uint_as_float(mask), 0.f);
-        }
-        // compact the entries that touch at least one sub-tile
-        const unsigned ball = __ballot_sync(0xffffffffu, mask != 0);
-        __syncthreads();                                    // previous chunk fully consumed
-        if (lane == 0) s_cnt[warp] = __popc(ball);
-        __syncthreads();
-        int off = 0, nc = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int c = s_cnt[w];
-            off += w < warp ? c : 0;
-            nc += c;
-        }
-        if (mask != 0) {
-            const int dst = off + __popc(ball & ((1u << lane) - 1u));
-            sP[dst] = P;
-            sC[dst] = C;
-        }
-        __syncthreads();
-
-        // ---- accumulate: every warp walks the chunk, skipping entries that miss its sub-tile
-        for (int e = 0; e < nc; ++e) {
-            const float4 c = sC[e];
-            if (!((__float_as_uint(c.z) >> warp) & 1u)) continue;
-            const float4 q = sP[e];
-            float ax0 = fmaf(-xf0, q.z, q.x), ax1 = fmaf(-xf1, q.z, q.x);
-            ax0 *= ax0; ax1 *= ax1;
-            float by0 = fmaf(-yf0, q.w, q.y), by1 = fmaf(-yf1, q.w, q.y), by2 = fmaf(-yf2, q.w, q.y), by3 = fmaf(-yf3, q.w, q.y);
-            by0 *= by0; by1 *= by1; by2 *= by2; by3 *= by3;
-            const float axs[2] = { ax0, ax1 };
-            const float bys[4] = { by0, by1, by2, by3 };
-#pragma unroll
-            for (int jx = 0; jx < 2; ++jx)
-#pragma unroll
-                for (int jy = 0; jy < 4; ++jy) {
-                    const float f = shape_eval<SHAPE>(fast_sqrt(axs[jx] + bys[jy]), a.tab);
-                    acc[0][jx * 4 + jy] = fmaf(c.x, f, acc[0][jx * 4 + jy]);
-                    if (NP > 1) acc[NP - 1][jx * 4 + jy] = fmaf(c.y, f, acc[NP - 1][jx * 4 + jy]);
-                }
-        }
-        // fold the chunk's float32 partial sums into the float64 accumulators
-#pragma unroll
-        for (int k = 0; k < NP; ++k)
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) { acc64[k][jj] += (double)acc[k][jj]; acc[k][jj] = 0.f; }
-    }
-
-    // ---- one read-modify-write of the tile (each pixel belongs to exactly one thread of one CTA)
-#pragma unroll
-    for (int jx = 0; jx < 2; ++jx) {
-        const int xi = X0 + xl + jx;
-        if (xi >= a.nx) continue;
-#pragma unroll
-        for (int jy = 0; jy < 4; ++jy) {
-            const int yi = Y0 + yl + jy;
-            if (yi >= a.ny) continue;
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
-                *o += acc64[k][jx * 4 + jy];
-            }
-        }
-    }
-}
-
-
-// K6 (warp-autonomous variant): the CTA still maps to one 32x32 tile, but every warp walks the tile's list on its own for
+// K6: the CTA maps to one 32x32 tile, but every warp walks the tile's list on its own for
 // its own sub-tile -- no CTA barrier anywhere.  Per 32 list entries: each lane stages one entry (float64 -> tile-relative
 // float32), tests it against the warp's sub-tile, the hits are compacted into the warp's private shared-memory slots with
 // a ballot, then all lanes evaluate the hits for their PX x PY pixel patch.  WX x WY warps tile the 32x32 pixels.
@@ -763,12 +640,12 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     return a;
 }
 
-// AST_ACCUM_VARIANT (tuning knob): 0 = CTA-cooperative staging, 1 = warp-autonomous 16x16 sub-tiles (4 warps, 2x4 pixels
-// per thread), 2 = warp-autonomous 8x16 sub-tiles (8 warps, 2x2 pixels per thread, default)
+// AST_ACCUM_VARIANT (tuning knob): 1 = 16x16 sub-tiles (4 warps, 2x4 pixels per thread), 2 = 8x16 sub-tiles (8 warps,
+// 2x2 pixels per thread; default: as fast at 36-pixel supports and faster below)
 static int accum_variant()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("AST_ACCUM_VARIANT"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; }
+    if (v < 0) { const char *e = getenv("AST_ACCUM_VARIANT"); v = e ? atoi(e) : 2; if (v != 1) v = 2; }
     return v;
 }
 
@@ -776,7 +653,6 @@ template <int SHAPE, int NP>
 static void launch_accum_np(const Acc &a, int64_t ntiles, cudaStream_t s)
 {
     switch (accum_variant()) {
-    case 0: tile_accum_kernel<SHAPE, NP><<<(unsigned)ntiles, kAccThreads, 0, s>>>(a); break;
     case 1: subtile_accum_kernel<SHAPE, NP, 2, 2, 2, 4><<<(unsigned)ntiles, 128, 0, s>>>(a); break;
     default: subtile_accum_kernel<SHAPE, NP, 4, 2, 2, 2><<<(unsigned)ntiles, 256, 0, s>>>(a); break;
     }

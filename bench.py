@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--h-mode", default="auto", choices=["auto", "uniform", "knn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time a footprint sweep (h scale 1/64 .. 1) and report it")
+    ap.add_argument("--sweep", action="store_true", help="full footprint sweep (h scale 1/64 .. 1) instead of the three default regimes")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the footprint regimes entirely")
     return ap.parse_args()
 
 
@@ -291,10 +292,12 @@ def main():
     # FP32 issue roofline of the accumulate stage: useful kernel evaluations (pixel, particle) pairs inside the support
     px_per_particle = float((np.pi * (2.0 * h_d.double().mean().item() * args.npix) ** 2))
     evals = N * px_per_particle
+    # 13.75 = SASS instructions per evaluated pixel in the full-shape loop of subtile_accum_kernel<cubic, 2 props> (9.75 in the
+    # outer-annulus loop); ncu: 87 % of the issue slots busy, 18.1 lane-instructions per useful update (profiles/r01_v2_summary.md)
     fp32 = {"pixel_updates_per_particle": px_per_particle, "updates_per_s": evals / (stage_ms[5] * 1e-3) if stage_ms[5] > 0 else None,
-            "lane_instr_per_update_sass": 13.25, "issue_peak_lane_instr_per_s": 148 * 4 * 32 * 1.965e9}
+            "lane_instr_per_evaluated_pixel_sass": 13.75, "issue_peak_lane_instr_per_s": 148 * 4 * 32 * 1.965e9}
     if fp32["updates_per_s"]:
-        fp32["issue_frac_at_max_clock"] = fp32["updates_per_s"] * 13.25 / fp32["issue_peak_lane_instr_per_s"]
+        fp32["useful_issue_frac_at_max_clock"] = fp32["updates_per_s"] * 13.75 / fp32["issue_peak_lane_instr_per_s"]
 
     # ---- end to end through the public host-buffer API (pinned host arrays in, numpy map out)
     e2e = None
@@ -320,10 +323,12 @@ def main():
                "h2d_bytes_per_step": int(world * N * (24 + 8 + 16)), "d2h_bytes_per_step": int(2 * size[0] * size[1] * 8),
                "ms_per_step": float(dt.item()) / args.steps * 1e3}
 
+    # footprint regimes: the same particle set with h scaled down; shows where the path is HBM-bound (sub-pixel supports,
+    # every particle deposited by the binning kernel) and where it is FP32-issue-bound (SPH-realistic supports)
     sweep = None
-    if args.sweep and rank == 0 and world == 1:
+    if not args.no_regimes and rank == 0 and world == 1:
         sweep = []
-        for sc in (1 / 64, 1 / 32, 1 / 16, 1 / 8, 1 / 4, 1 / 2, 1.0):
+        for sc in ((1 / 64, 1 / 32, 1 / 16, 1 / 8, 1 / 4, 1 / 2, 1.0) if args.sweep else (1 / 64, 1 / 8, 1.0)):
             hs = h_d * sc
             for _ in range(2):
                 eng.project(pos_d, hs, props_d, size, CoordinateAxes.Z, bounds, out=out)
@@ -358,7 +363,7 @@ def main():
             "cpu_baseline": cpu,
         }
         if sweep:
-            line["sweep"] = sweep
+            line["regimes"] = sweep
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
