@@ -30,7 +30,7 @@ struct KnnArgs {
     KnnGrid g;
     const double *xs, *ys, *zs;  // cell order
     const uint32_t *sidx;        // cell order -> original index
-    const uint32_t *cbeg, *cend;
+    const uint32_t *cstart;      // ncell + 1: particles of cell c are [cstart[c], cstart[c+1]) in cell order
     const uint32_t *qlist;       // nullable: sorted positions of the queries
     const double *qpos;          // EXTERNAL queries: (nq,3) row-major positions, output row = query index
     int64_t nq, q_begin;
@@ -58,7 +58,7 @@ __global__ void knn_key_kernel(const double *__restrict__ pos, int64_t n, KnnGri
 
 __global__ void knn_gather_kernel(const double *__restrict__ pos, const uint64_t *__restrict__ sorted, int64_t n,
                                   double *__restrict__ xs, double *__restrict__ ys, double *__restrict__ zs,
-                                  uint32_t *__restrict__ sidx, uint32_t *__restrict__ cbeg, uint32_t *__restrict__ cend,
+                                  uint32_t *__restrict__ sidx, uint32_t *__restrict__ cbeg,
                                   int64_t q_begin, int64_t q_end, uint32_t *__restrict__ qflag)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,8 +69,9 @@ __global__ void knn_gather_kernel(const double *__restrict__ pos, const uint64_t
     ys[s] = pos[3 * (int64_t)i + 1];
     zs[s] = pos[3 * (int64_t)i + 2];
     sidx[s] = i;
-    if (s == 0 || (uint32_t)(sorted[s - 1] >> 32) != key) cbeg[key] = (uint32_t)s;
-    if (s == n - 1 || (uint32_t)(sorted[s + 1] >> 32) != key) cend[key] = (uint32_t)(s + 1);
+    // per-cell counts from the run boundaries of the sorted keys (cbeg pre-zeroed): count = end - begin
+    if (s == n - 1 || (uint32_t)(sorted[s + 1] >> 32) != key) atomicAdd(&cbeg[key], (uint32_t)(s + 1));
+    if (s == 0 || (uint32_t)(sorted[s - 1] >> 32) != key) atomicSub(&cbeg[key], (uint32_t)s);
     if (qflag) qflag[s] = ((int64_t)i >= q_begin && (int64_t)i < q_end) ? 1u : 0u;
 }
 
@@ -131,6 +132,33 @@ __global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
         if (WANT_IDX) hp.id[i] = 0xffffffffu;
     }
 
+    double kth = INFINITY;                                      // heap root (current K-th smallest d2) kept in a register
+    // candidates j in [jb, je): contiguous particles of one or several consecutive cells of a z-column
+    auto scan_range = [&](uint32_t jb, uint32_t je) {
+        for (uint32_t j = jb; j < je; ++j) {
+            double ex = a.xs[j] - x, ey = a.ys[j] - y, ez = a.zs[j] - z;
+            if (per) {
+                if (ex < -g.half_box) ex += g.box; else if (ex > g.half_box) ex -= g.box;
+                if (ey < -g.half_box) ey += g.box; else if (ey > g.half_box) ey -= g.box;
+                if (ez < -g.half_box) ez += g.box; else if (ez > g.half_box) ez -= g.box;
+            }
+            const double d2 = AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez));
+            if (WANT_IDX) {
+                if (d2 <= kth) {                               // ties are ordered by index: look closer only then
+                    const uint32_t oj = a.sidx[j];
+                    if (hp.less(d2, oj, hp.d[0], hp.id[0])) { hp.replace_root(d2, oj); kth = hp.d[0]; }
+                }
+            } else if (d2 < kth) {
+                hp.replace_root(d2, 0u);
+                kth = hp.d[0];
+            }
+        }
+    };
+    // cells [z0, z1] (already inside [0, G)) of column (cx, cy): one contiguous particle range thanks to cstart
+    auto scan_cells = [&](int cx, int cy, int z0, int z1) {
+        const uint32_t base = ((uint32_t)cx * G + cy) * G;
+        scan_range(a.cstart[base + z0], a.cstart[base + z1 + 1]);
+    };
     for (int ring = 0;; ++ring) {
         for (int ox = -ring; ox <= ring; ++ox) {
             int cx = qc[0] + ox;
@@ -140,23 +168,25 @@ __global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
                 int cy = qc[1] + oy;
                 if (per) { if (2 * abs(oy) > G || (2 * abs(oy) == G && oy < 0)) continue; cy = (cy % G + G) % G; }
                 else if (cy < 0 || cy >= G) continue;
-                const bool inner = abs(ox) < ring && abs(oy) < ring;
-                for (int oz = -ring; oz <= ring; oz += (inner && ring > 0) ? 2 * ring : 1) {   // shell only
-                    int cz = qc[2] + oz;
-                    if (per) { if (2 * abs(oz) > G || (2 * abs(oz) == G && oz < 0)) continue; cz = (cz % G + G) % G; }
-                    else if (cz < 0 || cz >= G) continue;
-                    const uint32_t c = ((uint32_t)cx * G + cy) * G + cz;
-                    const uint32_t jb = a.cbeg[c], je = a.cend[c];
-                    for (uint32_t j = jb; j < je; ++j) {
-                        double ex = a.xs[j] - x, ey = a.ys[j] - y, ez = a.zs[j] - z;
-                        if (per) {
-                            if (ex < -g.half_box) ex += g.box; else if (ex > g.half_box) ex -= g.box;
-                            if (ey < -g.half_box) ey += g.box; else if (ey > g.half_box) ey -= g.box;
-                            if (ez < -g.half_box) ez += g.box; else if (ez > g.half_box) ez -= g.box;
-                        }
-                        const double d2 = AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez));
-                        const uint32_t oj = WANT_IDX ? a.sidx[j] : 0u;
-                        if (hp.less(d2, oj, hp.d[0], WANT_IDX ? hp.id[0] : 0u)) hp.replace_root(d2, oj);
+                if (abs(ox) == ring || abs(oy) == ring) {
+                    // outer column of the shell: the whole z-run [qz - ring, qz + ring], visited as contiguous ranges
+                    if (!per) {
+                        scan_cells(cx, cy, max(qc[2] - ring, 0), min(qc[2] + ring, G - 1));
+                    } else if (2 * ring + 1 >= G) {
+                        scan_cells(cx, cy, 0, G - 1);                        // the run wraps onto itself: every cell once
+                    } else {
+                        const int z0 = qc[2] - ring, z1 = qc[2] + ring;
+                        if (z0 < 0) { scan_cells(cx, cy, z0 + G, G - 1); scan_cells(cx, cy, 0, z1); }
+                        else if (z1 >= G) { scan_cells(cx, cy, z0, G - 1); scan_cells(cx, cy, 0, z1 - G); }
+                        else scan_cells(cx, cy, z0, z1);
+                    }
+                } else {
+                    // inner column: only the two caps oz = -ring, +ring
+                    for (int oz = -ring; oz <= ring; oz += 2 * ring) {
+                        int cz = qc[2] + oz;
+                        if (per) { if (2 * abs(oz) > G || (2 * abs(oz) == G && oz < 0)) continue; cz = (cz % G + G) % G; }
+                        else if (cz < 0 || cz >= G) continue;
+                        scan_cells(cx, cy, cz, cz);
                     }
                 }
             }
@@ -176,7 +206,7 @@ __global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
         }
         if (all) break;
         const double safe = dmin - 1e-9 * g.cs[0];
-        if (safe > 0.0 && hp.d[0] < safe * safe) break;
+        if (safe > 0.0 && kth < safe * safe) break;
     }
 
     const int64_t row = EXTERNAL ? t : (int64_t)a.sidx[s] - a.q_begin;
@@ -204,7 +234,7 @@ struct KnnLayout {
     int64_t ncell, nq;
     uint64_t *ea, *eb;
     double *xs, *ys, *zs;
-    uint32_t *sidx, *cbeg, *cend, *qflag, *qlist, *scan_tmp;
+    uint32_t *sidx, *cbeg, *qflag, *qlist, *scan_tmp, *cell_tmp;   // cbeg: ncell + 1 counts -> exclusive scan = cstart
     void *sort_ws;
     size_t bytes;
 };
@@ -223,7 +253,9 @@ static int knn_validate(const ast_knn_params *p)
 static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
 {
     KnnLayout L;
-    const double m = p->cell_target > 0 ? p->cell_target : (p->k / 3.0 > 2.0 ? p->k / 3.0 : 2.0);
+    // mean particles per cell; measured on B200 (benchmarks/knn_probe.py, k = 48, 256^3): 2 per cell is twice as fast as
+    // k/3 per cell (the explored cube of cells hugs the k-neighbour sphere more tightly; empty cells are cheap)
+    const double m = p->cell_target > 0 ? p->cell_target : 2.0;
     double g = floor(cbrt((double)(p->n > 0 ? p->n : 1) / m));
     L.G = g < 1 ? 1 : (g > 1000 ? 1000 : (int)g);
     L.ncell = (int64_t)L.G * L.G * L.G;
@@ -236,8 +268,8 @@ static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
     L.ys = c.take<double>(n);
     L.zs = c.take<double>(n);
     L.sidx = c.take<uint32_t>(n);
-    L.cbeg = c.take<uint32_t>(L.ncell);
-    L.cend = c.take<uint32_t>(L.ncell);
+    L.cbeg = c.take<uint32_t>(L.ncell + 1);
+    L.cell_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(L.ncell + 1));
     L.qflag = c.take<uint32_t>(n);
     L.qlist = c.take<uint32_t>(n);
     L.scan_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(n));
@@ -277,16 +309,16 @@ static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout
     int in_b = 0;
     AST_CUDA_TRY(radix_sort_u64(L.ea, L.eb, n, 32, ceil_log2_u64((uint64_t)L.ncell), L.sort_ws, s, &in_b));
     const uint64_t *sorted = in_b ? L.eb : L.ea;
-    AST_CUDA_TRY(cudaMemsetAsync(L.cbeg, 0, sizeof(uint32_t) * L.ncell, s));
-    AST_CUDA_TRY(cudaMemsetAsync(L.cend, 0, sizeof(uint32_t) * L.ncell, s));
-    knn_gather_kernel<<<nb, 256, 0, s>>>(pos, sorted, n, L.xs, L.ys, L.zs, L.sidx, L.cbeg, L.cend, q_begin, q_end,
+    AST_CUDA_TRY(cudaMemsetAsync(L.cbeg, 0, sizeof(uint32_t) * (L.ncell + 1), s));
+    knn_gather_kernel<<<nb, 256, 0, s>>>(pos, sorted, n, L.xs, L.ys, L.zs, L.sidx, L.cbeg, q_begin, q_end,
                                          subset ? L.qflag : nullptr);
+    AST_CUDA_TRY(scan_exclusive<uint32_t>(L.cbeg, L.ncell + 1, L.cell_tmp, nullptr, s));      // counts -> cstart
     if (subset) {
         AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n, L.scan_tmp, nullptr, s));
         knn_compact_kernel<<<nb, 256, 0, s>>>(L.qflag, L.sidx, n, q_begin, q_end, L.qlist);
     }
     a.g = g;
-    a.xs = L.xs; a.ys = L.ys; a.zs = L.zs; a.sidx = L.sidx; a.cbeg = L.cbeg; a.cend = L.cend;
+    a.xs = L.xs; a.ys = L.ys; a.zs = L.zs; a.sidx = L.sidx; a.cstart = L.cbeg;
     a.qlist = subset ? L.qlist : nullptr;
     a.qpos = nullptr;
     a.k = p->k;
