@@ -57,7 +57,7 @@ _lib = None
 # every symbol include/astro_sph_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = ["ast_project2d_workspace_bytes", "ast_project2d", "ast_bin2d", "ast_contrib_count2d", "ast_kernel_eval",
            "ast_sort_workspace_bytes", "ast_radix_sort_u64", "ast_grid3d_workspace_bytes", "ast_grid3d", "ast_bin3d",
-           "ast_knn_workspace_bytes", "ast_knn_h", "ast_knn_query", "ast_last_error", "ast_abi_version", "ast_tile_size",
+           "ast_knn_workspace_bytes", "ast_knn_h", "ast_knn_query", "ast_match_ids_workspace_bytes", "ast_match_ids", "ast_gather_rows", "ast_last_error", "ast_abi_version", "ast_tile_size",
            "ast_device_sm_count"]
 
 

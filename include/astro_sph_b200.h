@@ -188,6 +188,18 @@ int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_out, int32_t
 int ast_knn_query(const ast_knn_params *p, const double *data_pos, const double *query_pos, int64_t n_query,
                   double *dist_out, int32_t *idx_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- particle-ID matching, replaces the sort / intersect1d / searchsorted arithmetic of the reference's
+ * ArrayReorder family (tools/_ArrayReorder.py:744-768, :988-1038; used at io/EAGLE/_CatalogueSUBFIND.py:292-295):
+ * source_index_of_target[j] = index i of the source ID equal to target_ids[j] (smallest i if the source repeats an ID),
+ * or -1 (no match, or filtered out).  Filters (nullable): uint8 masks, 0 = the element does not take part.
+ * INT64_MIN is reserved.  All pointers are device pointers. */
+int ast_match_ids_workspace_bytes(int64_t n_source, size_t *bytes);
+int ast_match_ids(const int64_t *source_ids, int64_t n_source, const uint8_t *source_filter, const int64_t *target_ids,
+                  int64_t n_target, const uint8_t *target_filter, int64_t *source_index_of_target, void *workspace,
+                  size_t workspace_bytes, void *stream);
+/* out[j] = src[index[j]] for rows of row_bytes bytes where index[j] >= 0 (other rows untouched): applies a matching */
+int ast_gather_rows(const void *src, int64_t row_bytes, const int64_t *index, int64_t n_out, void *out, void *stream);
+
 /* ---- misc ---- */
 const char *ast_last_error(void);
 int ast_abi_version(void);
