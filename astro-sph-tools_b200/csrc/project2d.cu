@@ -129,7 +129,7 @@ __device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double 
 }
 
 // per-particle body of K1: classification, pair / large-h counts, direct deposit, record
-template <int SHAPE, bool DEPOSIT, int NP>
+template <int SHAPE, bool DEPOSIT, int NP, bool PER>
 __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0, double pb0, double h, double *coef /* [NP] props */,
                                              Rec *__restrict__ rec, uint32_t &npairs, uint32_t &nhuge)
 {
@@ -145,17 +145,18 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
         inv_hf = (float)inv_h;
         inv_h2 = (float)(inv_h * inv_h);
     }
+    const int n_img = PER ? p.n_img : 1;                       // compile-time 1 without periodic images
     const bool subpixel = p.small_max_px >= 4 && h2 * p.ax.inv_d <= 1.0 - 1e-9 && h2 * p.ay.inv_d <= 1.0 - 1e-9;
     if (subpixel) {
         if (DEPOSIT)
-            for (int m = 0; m < p.n_img; ++m)
-                deposit_subpixel<SHAPE, NP>(p, AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)),
-                                            AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m)), R2, inv_h2, coef);
+            for (int m = 0; m < n_img; ++m)
+                deposit_subpixel<SHAPE, NP>(p, AST_DADD(pa0, image_shift_a(n_img, p.box_a, m)),
+                                            AST_DADD(pb0, image_shift_b(n_img, p.box_b, m)), R2, inv_h2, coef);
         return;
     }
     bool need_rec = false;
-    for (int m = 0; m < p.n_img; ++m) {
-        const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
+    for (int m = 0; m < n_img; ++m) {
+        const double pa = AST_DADD(pa0, image_shift_a(n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(n_img, p.box_b, m));
         if (!may_touch(p.ax, pa, AST_DMUL(2.0, h)) || !may_touch(p.ay, pb, AST_DMUL(2.0, h))) continue;   // image cannot reach the map
         Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
         if (b.cls == CLS_SMALL) {
@@ -179,7 +180,7 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
 
 // K1.  DEPOSIT=false is the index-only variant used by ast_bin2d (NP is then irrelevant).  One particle per thread,
 // plain global loads; block b of the launch handles particle block b + block_offset.
-template <int SHAPE, bool DEPOSIT, int NP>
+template <int SHAPE, bool DEPOSIT, int NP, bool PER>
 __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
                                                           uint64_t *__restrict__ block_huge, int64_t block_offset)
 {
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict_
 #pragma unroll
             for (int k = 0; k < NP; ++k) coef[k] = p.prop[k][i];
         }
-        bin_particle<SHAPE, DEPOSIT, NP>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
+        bin_particle<SHAPE, DEPOSIT, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
     }
     // one reduction for both counts: per block pairs <= 256 * 9 * 256 < 2^20 and large-h entries <= 256 * 9 < 2^12
     const uint32_t packed = block_sum_u32((nhuge << 20) | npairs, red);
@@ -245,7 +246,7 @@ struct __align__(128) BinStage {
     double prop[NP][kBinThreads];
 };
 
-template <int SHAPE, int NP>
+template <int SHAPE, int NP, bool PER>
 __global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
                                                               uint64_t *__restrict__ block_huge, int64_t n_full_blocks)
 {
@@ -270,21 +271,24 @@ __global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restr
     };
     int64_t blk = blockIdx.x;
     if (tid == 0 && blk < n_full_blocks) issue(blk, 0);
-    uint32_t phase[2] = { 0u, 0u };
+    uint32_t phase_bits = 0u;                                   // bit s = parity to wait for on stage s (kept in a register)
     for (int it = 0; blk < n_full_blocks; blk += gridDim.x, ++it) {
         const int s = it & 1;
         const int64_t next = blk + gridDim.x;
         if (tid == 0 && next < n_full_blocks) issue(next, s ^ 1);     // stage s^1 was released by the barrier below
-        mbar_wait(&bar[s], phase[s]);
-        phase[s] ^= 1u;
+        mbar_wait(&bar[s], (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
         const int64_t i = blk * kBinThreads + tid;
         const double pa0 = st[s].pos[3 * tid + p.a_col], pb0 = st[s].pos[3 * tid + p.b_col], h = st[s].h[tid];
         double coef[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) coef[k] = st[s].prop[k][tid];
         uint32_t npairs = 0, nhuge = 0;
-        bin_particle<SHAPE, true, NP>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
-        const uint32_t packed = block_sum_u32((nhuge << 20) | npairs, red);     // contains the CTA barriers that release stage s
+        bin_particle<SHAPE, true, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
+        // one barrier-with-vote tells whether any thread has pairs / large-h entries at all (in the direct-deposit regime none
+        // has): only then pay for the full block reduction.  The barrier also releases stage s for the next bulk copy.
+        uint32_t packed = (nhuge << 20) | npairs;
+        if (__syncthreads_or(packed != 0u)) packed = block_sum_u32(packed, red);
         if (tid == 0) {
             block_pairs[blk] = packed & 0xfffffu;
             block_huge[blk] = packed >> 20;
@@ -701,8 +705,9 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     StageTimer tk((p->flags & AST_FLAG_TIMING) != 0, s);
     tk.begin(6);
     if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * a.map_stride * p->n_prop, s));
-    AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
-    AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    // entries 0..nb-1 are written by the binning kernels; only the sentinel entry nb (-> the totals after the scan) is zeroed
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs + L.nb, 0, sizeof(uint64_t), s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.block_huge + L.nb, 0, sizeof(uint64_t), s));
     tk.end();
     uint64_t totals[2] = { 0, 0 };
     if (p->n > 0) {
@@ -720,26 +725,38 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
                 cudaGetDevice(&dev);
                 cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
                 // persistent grid: one wave of resident CTAs (multiple of the SM count)
-#define AST_LAUNCH_TMA(SH, NPV)                                                                                         \
+#define AST_LAUNCH_TMA(SH, NPV, PERV)                                                                                       \
     do {                                                                                                                \
         int per_sm = 1;                                                                                                 \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_tma_kernel<SH, NPV>, kBinThreads, 0);                \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_tma_kernel<SH, NPV, PERV>, kBinThreads, 0);          \
         int64_t grid = (int64_t)sm * (per_sm > 0 ? per_sm : 1);                                                         \
         if (grid > n_full) grid = n_full;                                                                               \
-        bin_tma_kernel<SH, NPV><<<(unsigned)grid, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full);  \
+        bin_tma_kernel<SH, NPV, PERV><<<(unsigned)grid, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full); \
     } while (0)
-                if (a.shape == SHAPE_CUBIC) { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_CUBIC, 1); else AST_LAUNCH_TMA(SHAPE_CUBIC, 2); }
-                else if (a.shape == SHAPE_WENDLAND) { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_WENDLAND, 1); else AST_LAUNCH_TMA(SHAPE_WENDLAND, 2); }
-                else { if (p->n_prop == 1) AST_LAUNCH_TMA(SHAPE_TABLE, 1); else AST_LAUNCH_TMA(SHAPE_TABLE, 2); }
+                {
+                    const bool per = a.n_img > 1;
+#define AST_D2(SH) do { if (p->n_prop == 1) { if (per) AST_LAUNCH_TMA(SH, 1, true); else AST_LAUNCH_TMA(SH, 1, false); } \
+                        else { if (per) AST_LAUNCH_TMA(SH, 2, true); else AST_LAUNCH_TMA(SH, 2, false); } } while (0)
+                    if (a.shape == SHAPE_CUBIC) AST_D2(SHAPE_CUBIC);
+                    else if (a.shape == SHAPE_WENDLAND) AST_D2(SHAPE_WENDLAND);
+                    else AST_D2(SHAPE_TABLE);
+#undef AST_D2
+                }
 #undef AST_LAUNCH_TMA
                 st.n_launches += 1;
             }
             const int64_t n_rest = L.nb - n_full;
             if (n_rest > 0) {
-#define AST_LAUNCH_BIN(SH, NPV) bin_kernel<SH, true, NPV><<<(unsigned)n_rest, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full)
-                if (a.shape == SHAPE_CUBIC) { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_CUBIC, 1); else AST_LAUNCH_BIN(SHAPE_CUBIC, 2); }
-                else if (a.shape == SHAPE_WENDLAND) { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_WENDLAND, 1); else AST_LAUNCH_BIN(SHAPE_WENDLAND, 2); }
-                else { if (p->n_prop == 1) AST_LAUNCH_BIN(SHAPE_TABLE, 1); else AST_LAUNCH_BIN(SHAPE_TABLE, 2); }
+#define AST_LAUNCH_BIN(SH, NPV, PERV) bin_kernel<SH, true, NPV, PERV><<<(unsigned)n_rest, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full)
+                {
+                    const bool per = a.n_img > 1;
+#define AST_D2(SH) do { if (p->n_prop == 1) { if (per) AST_LAUNCH_BIN(SH, 1, true); else AST_LAUNCH_BIN(SH, 1, false); } \
+                        else { if (per) AST_LAUNCH_BIN(SH, 2, true); else AST_LAUNCH_BIN(SH, 2, false); } } while (0)
+                    if (a.shape == SHAPE_CUBIC) AST_D2(SHAPE_CUBIC);
+                    else if (a.shape == SHAPE_WENDLAND) AST_D2(SHAPE_WENDLAND);
+                    else AST_D2(SHAPE_TABLE);
+#undef AST_D2
+                }
 #undef AST_LAUNCH_BIN
                 st.n_launches += 1;
             }
@@ -838,7 +855,7 @@ extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
     if (p->n > 0) {
         if (bbox || cls) bbox_cls_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, bbox, cls);
-        bin_kernel<SHAPE_CUBIC, false, 1><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, 0);
+        bin_kernel<SHAPE_CUBIC, false, 1, true><<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, 0);
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
         AST_CUDA_TRY(cudaGetLastError());
