@@ -1,0 +1,44 @@
+"""-m gpu: randomized scenes (deterministic seeds) through the default path against the CPU oracle: image shapes, windows
+that cut the cloud, anisotropic pixels, all kernels, periodic or not, one or two weight fields, h spanning sub-pixel to
+many tiles.  Gates: relative L2 <= 1e-5, total <= 1e-6 (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["cubic_spline_3d", "wendland_c2_2d", "wendland_c2_3d", "cubic_spline_2d"]
+
+
+def scene(seed):
+    rng = np.random.default_rng(seed)
+    nx, ny = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+    L = 10.0
+    x0, y0 = rng.uniform(-2, 4, 2)
+    wx, wy = rng.uniform(2, 12, 2)
+    n = int(rng.integers(1, 6000))
+    pos = rng.uniform(0, L, (n, 3))
+    px = max(wx / nx, wy / ny)
+    h = np.exp(rng.uniform(np.log(0.05 * px), np.log(min(40 * px, 6.0)), n))
+    h[rng.random(n) < 0.02] = 0.0
+    props = [rng.normal(size=n), rng.uniform(0.1, 2.0, n)][: int(rng.integers(1, 3))]
+    return dict(pos=pos, h=h, props=props, size=(nx, ny), bounds=(x0, x0 + wx, y0, y0 + wy), axis=int(rng.integers(0, 3)),
+                kernel=KERNELS[int(rng.integers(0, 4))], periodic=bool(rng.random() < 0.35), L=L)
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_scene(oracle, seed):
+    from gpu_util import gpu_project
+    s = scene(seed)
+    box = (s["L"], s["L"]) if s["periodic"] else None
+    ref = oracle.project2d(s["pos"], s["h"], np.stack(s["props"]), s["size"], s["axis"], *s["bounds"], kernel=s["kernel"],
+                           periodic=s["periodic"], box=box)
+    m, st = gpu_project(s["pos"], s["h"], s["props"], s["size"], s["axis"], s["bounds"], kernel=s["kernel"], periodic=s["periodic"], box=box)
+    assert m.shape == ref.shape
+    for k in range(len(s["props"])):
+        if np.abs(ref[k]).sum() == 0:
+            assert not m[k].any()
+            continue
+        assert rel_l2(m[k], ref[k]) <= 1e-5, (seed, k, st)
+        assert abs(m[k].sum() - ref[k].sum()) <= 1e-6 * np.abs(ref[k]).sum(), (seed, k, st)
