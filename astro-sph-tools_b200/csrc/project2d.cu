@@ -511,6 +511,199 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
     }
 }
 
+// K6, default variant: same warp-autonomous scheme (8 warps, 8x16 sub-tile per warp, 2x2 pixels per thread), but for
+// batches with enough hits the lane that staged an entry also computes the entry's squared x-distances to the 8 pixel
+// columns and squared y-distances to the 16 pixel rows of the sub-tile (in units of h) and stores them with the
+// weights: the evaluating lanes then fetch their two column and two row values (LDS.64 + LDS.128) instead of
+// recomputing them 32 lanes wide, and the per-pixel work is FADD, MUFU.SQRT, shape, NP FFMA.  The cubic spline is
+// evaluated as f/2 = min(1/2 + s(3q/8 - 3/4), sat(1 - q/2)^3), s = q^2 (the first argument is the inner branch
+// 1 - 3/2 q^2 + 3/4 q^3 of _kernels.pyx:17, the second the outer branch 1/4 (2-q)^3 of :19; inner - outer = -(1-q)^3/2
+// changes sign exactly at q = 1, so the minimum selects the right branch and is 0 beyond q = 2), with the weights
+// doubled at staging time.  Sparse batches (fewer than kRowColMinHits hits) take the classic per-lane coordinates.
+constexpr int kRowColMinHits = 8;
+struct __align__(16) RowColSlot {
+    float4 ax[2];        // squared x-distance (in h) to the 8 pixel columns of the sub-tile
+    float4 byc[8];       // {squared y-distance to rows 2j, 2j+1, c0, c1}
+};
+static_assert(sizeof(RowColSlot) == 160, "slot layout");
+
+template <int SHAPE>
+__device__ __forceinline__ float shape_half_full(float s, const ShapeTab &tab)
+{
+    const float q = fast_sqrt(s);
+    if (SHAPE == SHAPE_CUBIC) {
+        const float p = fmaf(s, fmaf(0.375f, q, -0.75f), 0.5f);
+        const float a1 = __saturatef(fmaf(q, -0.5f, 1.0f));
+        return fminf(p, a1 * a1 * a1);
+    }
+    return shape_eval<SHAPE>(q, tab);
+}
+__device__ __forceinline__ float shape_half_outer(float s)
+{
+    const float a1 = __saturatef(fmaf(fast_sqrt(s), -0.5f, 1.0f));
+    return a1 * a1 * a1;
+}
+
+template <int SHAPE, int NP>
+__global__ void __launch_bounds__(256, 4) rowcol_accum_kernel(Acc a)
+{
+    constexpr int NW = 8, WY = 2, SX = 8, SY = 16, PX = 2, PY = 2, LY = SY / PY, NPIX = PX * PY;
+    __shared__ RowColSlot sS[NW][32];
+
+    const int tile = blockIdx.x;
+    const uint32_t beg = a.tbeg[tile], cnt = a.tend[tile] - beg;
+    const uint32_t total = cnt + a.n_huge;
+    if (total == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tile / a.nty, ty = tile - tx * a.nty;
+    const int X0 = tx * TILE, Y0 = ty * TILE;
+    const int sub_x = SX * (warp / WY), sub_y = SY * (warp % WY);
+    const int xl = sub_x + PX * (lane / LY), yl = sub_y + PY * (lane % LY);
+    const float xf[PX] = { (float)xl, (float)(xl + 1) }, yf[PY] = { (float)yl, (float)(yl + 1) };
+    const float lox = (float)sub_x, hix = (float)(sub_x + SX - 1), loy = (float)sub_y, hiy = (float)(sub_y + SY - 1);
+    const float dxf = (float)a.dx, dyf = (float)a.dy;
+    const double ox = (double)X0, oy = (double)Y0;
+    RowColSlot *const slots = sS[warp];
+    // classic view of the same storage: {ux*sx, uy*sy, sx, sy} in ax[0], {c0, c1} in the first half of ax[1]
+    const float cscale = SHAPE == SHAPE_CUBIC ? 2.0f : 1.0f;
+
+    float acc[NP][NPIX];
+    double acc64[NP][NPIX];
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+#pragma unroll
+        for (int j = 0; j < NPIX; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
+
+    int since_fold = 0;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        bool hit = false, outer = false;
+        float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 C = make_float2(0.f, 0.f);
+        if (j < total) {
+            uint32_t idx, m;
+            if (j < cnt) {
+                const uint64_t e = a.sorted[beg + j];
+                idx = (uint32_t)e;
+                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
+            } else {
+                const uint64_t e = a.huge[j - cnt];
+                idx = (uint32_t)e;
+                m = (uint32_t)(e >> 32);
+            }
+            const Rec r = a.rec[idx];
+            const float fx = (float)((r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox);
+            const float fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
+            const float sx = dxf * r.inv_h, sy = dyf * r.inv_h;
+            const float ddx = fmaxf(fmaxf(lox - fx, fx - hix), 0.f) * sx;
+            const float ddy = fmaxf(fmaxf(loy - fy, fy - hiy), 0.f) * sy;
+            const float qmin2 = ddx * ddx + ddy * ddy;
+            hit = qmin2 < 4.0001f;
+            outer = hit && SHAPE == SHAPE_CUBIC && qmin2 >= 1.0f;
+            P = make_float4(fx * sx, fy * sy, sx, sy);
+            C = make_float2(cscale * r.c[0], NP > 1 ? cscale * r.c[1] : 0.f);
+        }
+        const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
+        const unsigned ball_o = __ballot_sync(0xffffffffu, outer);
+        const int nf = __popc(ball_f), no = __popc(ball_o), nh = nf + no;
+        if (nh == 0) continue;
+        const unsigned lt = (1u << lane) - 1u;
+        const int dst = outer ? 31 - __popc(ball_o & lt) : __popc(ball_f & lt);
+        if (nh >= kRowColMinHits) {
+            if (hit) {
+                RowColSlot *d = slots + dst;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float t = fmaf(-(lox + (float)i), P.z, P.x); v[i] = t * t; }
+                d->ax[0] = make_float4(v[0], v[1], v[2], v[3]);
+                d->ax[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float t0 = fmaf(-(loy + (float)(2 * i)), P.w, P.y), t1 = fmaf(-(loy + (float)(2 * i + 1)), P.w, P.y);
+                    d->byc[i] = make_float4(t0 * t0, t1 * t1, C.x, C.y);
+                }
+            }
+            __syncwarp();
+            for (int e = 0; e < nf; ++e) {
+                const float2 ax2 = reinterpret_cast<const float2 *>(slots[e].ax)[lane >> 3];
+                const float4 bc = slots[e].byc[lane & 7];
+                const float s00 = ax2.x + bc.x, s01 = ax2.x + bc.y, s10 = ax2.y + bc.x, s11 = ax2.y + bc.y;
+                const float f00 = shape_half_full<SHAPE>(s00, a.tab), f01 = shape_half_full<SHAPE>(s01, a.tab);
+                const float f10 = shape_half_full<SHAPE>(s10, a.tab), f11 = shape_half_full<SHAPE>(s11, a.tab);
+                acc[0][0] = fmaf(bc.z, f00, acc[0][0]); acc[0][1] = fmaf(bc.z, f01, acc[0][1]);
+                acc[0][2] = fmaf(bc.z, f10, acc[0][2]); acc[0][3] = fmaf(bc.z, f11, acc[0][3]);
+                if (NP > 1) {
+                    acc[NP - 1][0] = fmaf(bc.w, f00, acc[NP - 1][0]); acc[NP - 1][1] = fmaf(bc.w, f01, acc[NP - 1][1]);
+                    acc[NP - 1][2] = fmaf(bc.w, f10, acc[NP - 1][2]); acc[NP - 1][3] = fmaf(bc.w, f11, acc[NP - 1][3]);
+                }
+            }
+            if (SHAPE == SHAPE_CUBIC) {
+                for (int e = 32 - no; e < 32; ++e) {
+                    const float2 ax2 = reinterpret_cast<const float2 *>(slots[e].ax)[lane >> 3];
+                    const float4 bc = slots[e].byc[lane & 7];
+                    const float f00 = shape_half_outer(ax2.x + bc.x), f01 = shape_half_outer(ax2.x + bc.y);
+                    const float f10 = shape_half_outer(ax2.y + bc.x), f11 = shape_half_outer(ax2.y + bc.y);
+                    acc[0][0] = fmaf(bc.z, f00, acc[0][0]); acc[0][1] = fmaf(bc.z, f01, acc[0][1]);
+                    acc[0][2] = fmaf(bc.z, f10, acc[0][2]); acc[0][3] = fmaf(bc.z, f11, acc[0][3]);
+                    if (NP > 1) {
+                        acc[NP - 1][0] = fmaf(bc.w, f00, acc[NP - 1][0]); acc[NP - 1][1] = fmaf(bc.w, f01, acc[NP - 1][1]);
+                        acc[NP - 1][2] = fmaf(bc.w, f10, acc[NP - 1][2]); acc[NP - 1][3] = fmaf(bc.w, f11, acc[NP - 1][3]);
+                    }
+                }
+            }
+        } else {
+            if (hit) {
+                slots[dst].ax[0] = P;
+                *reinterpret_cast<float2 *>(&slots[dst].ax[1]) = C;
+            }
+            __syncwarp();
+            // sparse batch: full and outer-annulus hits alike through the general shape
+            for (int e = 0; e < nh; ++e) {
+                const int sl = e < nf ? e : 32 - nh + e;
+                const float4 q = slots[sl].ax[0];
+                const float2 c = *reinterpret_cast<const float2 *>(&slots[sl].ax[1]);
+                float ax2[PX], by2[PY];
+#pragma unroll
+                for (int i = 0; i < PX; ++i) { const float t = fmaf(-xf[i], q.z, q.x); ax2[i] = t * t; }
+#pragma unroll
+                for (int i = 0; i < PY; ++i) { const float t = fmaf(-yf[i], q.w, q.y); by2[i] = t * t; }
+#pragma unroll
+                for (int ix = 0; ix < PX; ++ix)
+#pragma unroll
+                    for (int iy = 0; iy < PY; ++iy) {
+                        const float f = shape_half_full<SHAPE>(ax2[ix] + by2[iy], a.tab);
+                        acc[0][ix * PY + iy] = fmaf(c.x, f, acc[0][ix * PY + iy]);
+                        if (NP > 1) acc[NP - 1][ix * PY + iy] = fmaf(c.y, f, acc[NP - 1][ix * PY + iy]);
+                    }
+            }
+        }
+        __syncwarp();
+        since_fold += nh;
+        if (since_fold >= 96) {
+            since_fold = 0;
+#pragma unroll
+            for (int k = 0; k < NP; ++k)
+#pragma unroll
+                for (int jj = 0; jj < NPIX; ++jj) { acc64[k][jj] += (double)acc[k][jj]; acc[k][jj] = 0.f; }
+        }
+    }
+#pragma unroll
+    for (int ix = 0; ix < PX; ++ix) {
+        const int xi = X0 + xl + ix;
+        if (xi >= a.nx) continue;
+#pragma unroll
+        for (int iy = 0; iy < PY; ++iy) {
+            const int yi = Y0 + yl + iy;
+            if (yi >= a.ny) continue;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
+                *o += acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
+            }
+        }
+    }
+}
+
 // exact contributor count (reference mask) per pixel, for parity tests
 __global__ void contrib_count_kernel(P2 p, int32_t *__restrict__ count)
 {
@@ -645,11 +838,11 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
 }
 
 // AST_ACCUM_VARIANT (tuning knob): 1 = 16x16 sub-tiles (4 warps, 2x4 pixels per thread), 2 = 8x16 sub-tiles (8 warps,
-// 2x2 pixels per thread; default: as fast at 36-pixel supports and faster below)
+// 2x2 pixels per thread, coordinates per lane), 3 = default: 8x16 sub-tiles with staged row/column distances
 static int accum_variant()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("AST_ACCUM_VARIANT"); v = e ? atoi(e) : 2; if (v != 1) v = 2; }
+    if (v < 0) { const char *e = getenv("AST_ACCUM_VARIANT"); v = e ? atoi(e) : 3; if (v < 1 || v > 3) v = 3; }
     return v;
 }
 
@@ -658,6 +851,7 @@ static void launch_accum_np(const Acc &a, int64_t ntiles, cudaStream_t s)
 {
     switch (accum_variant()) {
     case 1: subtile_accum_kernel<SHAPE, NP, 2, 2, 2, 4><<<(unsigned)ntiles, 128, 0, s>>>(a); break;
+    case 3: rowcol_accum_kernel<SHAPE, NP><<<(unsigned)ntiles, 256, 0, s>>>(a); break;
     default: subtile_accum_kernel<SHAPE, NP, 4, 2, 2, 2><<<(unsigned)ntiles, 256, 0, s>>>(a); break;
     }
 }

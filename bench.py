@@ -288,16 +288,21 @@ def main():
     roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
                 "kernel_ms": float(stage_ms[dom]),
-                "note": "h = d_48 footprints (~4000 pixel updates per particle) make this stage FP32-issue-bound; see fp32 key"}
+                "note": "h = d_48 footprints (~4000 pixel updates per particle) make this stage FP32-issue/MUFU-bound; see fp32 key"}
     # FP32 issue roofline of the accumulate stage: useful kernel evaluations (pixel, particle) pairs inside the support
     px_per_particle = float((np.pi * (2.0 * h_d.double().mean().item() * args.npix) ** 2))
     evals = N * px_per_particle
-    # 13.75 = SASS instructions per evaluated pixel in the full-shape loop of subtile_accum_kernel<cubic, 2 props> (9.75 in the
-    # outer-annulus loop); ncu: 87 % of the issue slots busy, 18.1 lane-instructions per useful update (profiles/r01_v2_summary.md)
+    # rowcol_accum_kernel<cubic, 2 props>: 10.6 SASS instructions per evaluated pixel in the full-shape loop, 7.6 in the
+    # outer-annulus loop, one MUFU.SQRT each.  Two ceilings for USEFUL updates (pixels inside the support): the issue
+    # ceiling at the full-loop instruction count, and the MUFU ceiling (16 sqrt per clock per SM, measured by
+    # benchmarks/micro/ffma2_probe.cu: 8 cycles per warp-wide MUFU.SQRT) -- every update needs exactly one square root.
+    sm_hz = 148 * 1.965e9
     fp32 = {"pixel_updates_per_particle": px_per_particle, "updates_per_s": evals / (stage_ms[5] * 1e-3) if stage_ms[5] > 0 else None,
-            "lane_instr_per_evaluated_pixel_sass": 13.75, "issue_peak_lane_instr_per_s": 148 * 4 * 32 * 1.965e9}
+            "lane_instr_per_evaluated_pixel_sass": {"full": 10.6, "outer_annulus": 7.6},
+            "issue_peak_lane_instr_per_s": sm_hz * 4 * 32, "mufu_peak_sqrt_per_s": sm_hz * 16}
     if fp32["updates_per_s"]:
-        fp32["useful_issue_frac_at_max_clock"] = fp32["updates_per_s"] * 13.75 / fp32["issue_peak_lane_instr_per_s"]
+        fp32["useful_issue_frac_at_max_clock"] = fp32["updates_per_s"] * 10.6 / fp32["issue_peak_lane_instr_per_s"]
+        fp32["useful_mufu_frac_at_max_clock"] = fp32["updates_per_s"] / fp32["mufu_peak_sqrt_per_s"]
 
     # ---- end to end through the public host-buffer API (pinned host arrays in, numpy map out)
     e2e = None
