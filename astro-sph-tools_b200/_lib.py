@@ -48,6 +48,16 @@ class KnnParams(C.Structure):
                 ("q_begin", C.c_int64), ("q_count", C.c_int64)]
 
 
+TABLE_MAX_DIM = 4
+TABLE_POW10 = 1
+
+
+class TableParams(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("shape", C.c_int32 * TABLE_MAX_DIM), ("axes", C.c_void_p * TABLE_MAX_DIM),
+                ("table", C.c_void_p), ("fill_value", C.c_double), ("fixed_dim", C.c_int32), ("flags", C.c_int32),
+                ("fixed_value", C.c_double)]
+
+
 class WorkspaceError(RuntimeError):
     """AST_EWORKSPACE: a capacity or the workspace was too small (message says what is needed)."""
 
@@ -57,7 +67,8 @@ _lib = None
 # every symbol include/astro_sph_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = ["ast_project2d_workspace_bytes", "ast_project2d", "ast_bin2d", "ast_contrib_count2d", "ast_kernel_eval",
            "ast_sort_workspace_bytes", "ast_radix_sort_u64", "ast_grid3d_workspace_bytes", "ast_grid3d", "ast_bin3d",
-           "ast_knn_workspace_bytes", "ast_knn_h", "ast_knn_query", "ast_match_ids_workspace_bytes", "ast_match_ids", "ast_gather_rows", "ast_last_error", "ast_abi_version", "ast_tile_size",
+           "ast_knn_workspace_bytes", "ast_knn_h", "ast_knn_query", "ast_match_ids_workspace_bytes", "ast_match_ids", "ast_gather_rows", "ast_table_interp",
+           "ast_last_error", "ast_abi_version", "ast_tile_size",
            "ast_device_sm_count"]
 
 

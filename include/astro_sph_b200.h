@@ -200,6 +200,30 @@ int ast_match_ids(const int64_t *source_ids, int64_t n_source, const uint8_t *so
 /* out[j] = src[index[j]] for rows of row_bytes bytes where index[j] >= 0 (other rows untouched): applies a matching */
 int ast_gather_rows(const void *src, int64_t row_bytes, const int64_t *index, int64_t n_out, void *out, void *stream);
 
+/* ---- N-D linear table interpolation and fused per-particle weights, replaces
+ * IonisationTableBase.__call__ / evaluate_at_redshift (data_structures/_IonisationTable.py:44-58: scipy
+ * RegularGridInterpolator, method "linear", bounds_error=False, fill_value=-inf; HM01 tables loaded at
+ * io/ionisation_tables/_HM01.py:73-97).  Bit-equal to scipy in float64.  Coordinates come as one device pointer and element
+ * stride per dimension, so an (N,ndim) row-major gas_state (x_cols[d] = gas_state + d, stride ndim) and separate
+ * per-particle arrays (stride 1) are both served without a copy; dimension `fixed_dim` (>= 0) takes `fixed_value` for every
+ * point (evaluate_at_redshift).  out[i] = value, or 10^value with AST_TABLE_POW10, times base[i] when base is not null
+ * (element mass x ion fraction = the weight array of an ion column-density map; outside the table 10^-inf = 0). */
+#define AST_TABLE_MAX_DIM 4
+enum { AST_TABLE_POW10 = 1 };
+typedef struct ast_table_params {
+    int32_t ndim;                              /* 1..AST_TABLE_MAX_DIM */
+    int32_t shape[AST_TABLE_MAX_DIM];          /* grid points per dimension, each >= 2 */
+    const double *axes[AST_TABLE_MAX_DIM];     /* device: ascending grid coordinates of each dimension */
+    const double *table;                       /* device: values, C order (dimension 0 slowest) */
+    double fill_value;                         /* result outside the grid (the reference uses -inf) */
+    int32_t fixed_dim;                         /* -1, or the dimension held at fixed_value */
+    int32_t flags;                             /* AST_TABLE_POW10 */
+    double fixed_value;
+} ast_table_params;
+int ast_table_interp(const ast_table_params *t, const double *const *x_cols /* host array of ndim device pointers */,
+                     const int64_t *x_strides /* host, in elements */, int64_t n, const double *base /* nullable */,
+                     double *out, void *stream);
+
 /* ---- misc ---- */
 const char *ast_last_error(void);
 int ast_abi_version(void);

@@ -243,3 +243,50 @@ def reference_module():
     mod = importlib.import_module("astro_sph_tools.tools.projections")
     axes = importlib.import_module("astro_sph_tools._CoordinateAxes")
     return mod, axes.CoordinateAxes
+
+
+# ---- N-D linear table interpolation ----------------------------------------------------------------
+def table_interp(table, axes, x, fill_value=-np.inf):
+    """numpy restatement of what IonisationTableBase.__call__ computes (reference data_structures/_IonisationTable.py:44-52:
+    scipy.interpolate.RegularGridInterpolator(axes, table, bounds_error=False, fill_value=-inf)(x)).  The arithmetic lives
+    in scipy (third party, un-pinned by the reference, 1.18.1 in this image): interval search of _rgi_cython.find_indices,
+    corner sum of _rgi.py:_evaluate_linear in itertools.product order, then fill and NaN overrides of __call__.
+    Pinned bit-for-bit against scipy itself in tests/test_table_oracle_cpu.py.  x: (N, ndim)."""
+    import itertools
+    table = np.asarray(table, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64).reshape(-1, table.ndim)
+    idx, y = [], []
+    nan = np.any(np.isnan(x), axis=1)
+    oob = np.zeros(x.shape[0], dtype=bool)
+    for d, g in enumerate(axes):
+        g = np.asarray(g, dtype=np.float64)
+        xd = x[:, d]
+        oob |= (xd < g[0]) | (xd > g[-1])
+        i = np.clip(np.searchsorted(g, xd, side="right") - 1, 0, len(g) - 2)      # x[i] <= xval < x[i+1], edges clamped
+        with np.errstate(invalid="ignore"):
+            y.append((xd - g[i]) / (g[i + 1] - g[i]))
+        idx.append(i)
+    value = np.zeros(x.shape[0])
+    with np.errstate(invalid="ignore"):
+        if table.ndim == 2:
+            # scipy's compiled 2-D fast path (_rgi_cython.evaluate_linear_2d, taken by _rgi.py __call__ for 2-D float64
+            # tables) associates differently: (v * w0) * w1, summed left to right without the leading zero
+            (i0, i1), (y0, y1) = idx, y
+            value = (table[i0, i1] * (1 - y0) * (1 - y1) + table[i0, i1 + 1] * (1 - y0) * y1
+                     + table[i0 + 1, i1] * y0 * (1 - y1) + table[i0 + 1, i1 + 1] * y0 * y1)
+        else:
+            for corner in itertools.product((0, 1), repeat=table.ndim):
+                w = np.ones(x.shape[0])
+                for d, up in enumerate(corner):
+                    w = w * (y[d] if up else 1 - y[d])
+                value = value + table[tuple(idx[d] + up for d, up in enumerate(corner))] * w
+    value = np.asarray(value, dtype=np.float64)
+    value[oob] = fill_value
+    value[nan] = np.nan
+    return value
+
+
+def table_interp_scipy(table, axes, x, fill_value=-np.inf):
+    """the call the reference makes (_IonisationTable.py:44-52)"""
+    from scipy.interpolate import RegularGridInterpolator
+    return RegularGridInterpolator(tuple(axes), table, bounds_error=False, fill_value=fill_value)(x)
