@@ -4,3 +4,4 @@ from ._kernels import (quartic_spline_kernel, wendland_c2_kernel, wendland_c2_ke
                        kernel_id_of, TabulatedKernel)
 from ._engine import Projector2D
 from ._gridder import create_grid, Gridder3D, default_gridder
+from ._ingest import strip_units, pinned, snapshot_maps

@@ -142,7 +142,8 @@ class Projector2D:
         n = int(positions.shape[0])
         nb = max(1, min(16, -(-n // int(batch_particles)))) if n > 0 else 1
         if nb == 1:
-            to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+            # float32 host arrays (the ingestion shim's opt-in) cross PCIe as float32 and are widened on the device: exact
+            to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True).to(torch.float64)
             pos_d, h_d = to_dev(positions), to_dev(smoothing_lengths)
             props_d = [to_dev(q) for q in plist]
             out = self.project(pos_d, h_d, props_d[0] if single else props_d, image_size, axis, bounds, kernel, periodic, box,
@@ -178,10 +179,17 @@ class Projector2D:
                     with torch.cuda.stream(copy):
                         if b >= 2:
                             copy.wait_event(free[k])
-                        st["pos"][:m].copy_(torch.from_numpy(positions[lo:hi]), non_blocking=True)
-                        st["h"][:m].copy_(torch.from_numpy(smoothing_lengths[lo:hi]), non_blocking=True)
+
+                        def put(dst, src):
+                            src = torch.from_numpy(src)
+                            if src.dtype == torch.float64:
+                                dst.copy_(src, non_blocking=True)
+                            else:         # float32 over PCIe, widened on the device (a cross-dtype copy_ would convert on the CPU)
+                                dst.copy_(src.to(dev, non_blocking=True))
+                        put(st["pos"][:m], positions[lo:hi])
+                        put(st["h"][:m], smoothing_lengths[lo:hi])
                         for dst, src in zip(st["props"], plist):
-                            dst[:m].copy_(torch.from_numpy(src[lo:hi]), non_blocking=True)
+                            put(dst[:m], src[lo:hi])
                         ready[k].record(copy)
                     compute.wait_event(ready[k])
                     self.project(st["pos"][:m], st["h"][:m], [q[:m] for q in st["props"]], image_size, axis, bounds, kernel,

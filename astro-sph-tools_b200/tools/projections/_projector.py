@@ -33,23 +33,25 @@ def default_projector(device=None):
     return _default[key]
 
 
-def _check_buffer(a, ndim, name):
+def _check_buffer(a, ndim, name, allow_float32=False):
     """Same failures as the reference's Cython typed memoryviews (double[:, :] / double[:])."""
     if hasattr(a, "value") and not isinstance(a, np.ndarray):      # unyt_array-like without importing unyt
         a = a.value
     a = np.asarray(a) if not isinstance(a, np.ndarray) else a
     if a.ndim != ndim:
         raise ValueError(f"Buffer has wrong number of dimensions (expected {ndim}, got {a.ndim})")
+    if a.dtype == np.float32 and allow_float32:
+        return np.asarray(a)
     if a.dtype != np.float64:
         got = {"float32": "float", "int64": "long", "int32": "int"}.get(a.dtype.name, a.dtype.name)
         raise ValueError(f"Buffer dtype mismatch, expected 'double' but got '{got}'")
     return np.asarray(a)
 
 
-def _validate(positions, smoothing_lengths, props):
-    positions = _check_buffer(positions, 2, "positions")
-    smoothing_lengths = _check_buffer(smoothing_lengths, 1, "smoothing_lengths")
-    props = [_check_buffer(q, 1, "particle_properties") for q in props]
+def _validate(positions, smoothing_lengths, props, allow_float32=False):
+    positions = _check_buffer(positions, 2, "positions", allow_float32)
+    smoothing_lengths = _check_buffer(smoothing_lengths, 1, "smoothing_lengths", allow_float32)
+    props = [_check_buffer(q, 1, "particle_properties", allow_float32) for q in props]
     n = positions.shape[0]
     if positions.shape[1] != 3:
         raise ValueError(f"positions must have shape (N, 3), got {positions.shape}")
@@ -74,10 +76,13 @@ def create_image(
     periodic: bool = False,
     box_size=None,
     device=None,
+    allow_float32: bool = False,
 ) -> np.ndarray:
-    """SPH-kernel-weighted projection of particles onto a 2-D map (see module docstring)."""
+    """SPH-kernel-weighted projection of particles onto a 2-D map (see module docstring).
+    allow_float32=True (extension): float32 arrays, as stored on disk, are accepted, sent over PCIe as float32 and widened
+    on the device -- the result equals passing ``a.astype(numpy.float64)``; the default rejects them like the reference."""
     kernel = kernel_id_of(kernel_func)
-    positions, smoothing_lengths, props = _validate(positions, smoothing_lengths, [particle_properties])
+    positions, smoothing_lengths, props = _validate(positions, smoothing_lengths, [particle_properties], allow_float32)
     eng = default_projector(device)
     return eng.project_host(positions, smoothing_lengths, props[0], image_size, projection_axis,
                             (x_min, x_max, y_min, y_max), kernel, periodic, box_size)
@@ -99,11 +104,12 @@ def create_images(
     periodic: bool = False,
     box_size=None,
     device=None,
+    allow_float32: bool = False,
 ) -> np.ndarray:
     """Extension: several weight arrays (e.g. mass and mass*T) deposited in ONE pass over the particles.
     Returns (P, nx, ny); row p equals create_image(..., particle_properties[p], ...)."""
     kernel = kernel_id_of(kernel_func)
-    positions, smoothing_lengths, props = _validate(positions, smoothing_lengths, list(particle_properties))
+    positions, smoothing_lengths, props = _validate(positions, smoothing_lengths, list(particle_properties), allow_float32)
     eng = default_projector(device)
     from ... import _lib
     outs = []

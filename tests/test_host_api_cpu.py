@@ -99,3 +99,19 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "liboracle" not in src, f
+
+
+def test_strip_units_is_a_view_without_importing_unyt():
+    from astro_sph_tools_b200.tools.projections import strip_units
+
+    class U(np.ndarray):
+        pass
+
+    a = np.arange(6.0).reshape(2, 3).view(U)
+    a.units = "Mpc"
+    v = strip_units(a)
+    assert type(v) is np.ndarray and np.shares_memory(v, a)
+
+    class Q:                      # unyt_quantity-like: only .value
+        value = np.ones(3)
+    assert np.array_equal(strip_units(Q()), np.ones(3))
