@@ -92,6 +92,28 @@ __device__ __forceinline__ float fast_sqrt(float x)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// Deposition-loop forms taking s = q^2 and returning f/2 for the cubic spline (the factor 2 is folded into the weights at
+// staging time) and f for the other shapes:
+//   cubic: f/2 = min(1/2 + s (3q/8 - 3/4), sat(1 - q/2)^3).  The first argument is the inner branch 1 - 3/2 q^2 + 3/4 q^3 of
+//   _kernels.pyx:17 (halved), the second the outer branch 1/4 (2-q)^3 of :19 (halved); inner - outer = -(1-q)^3 / 2 changes
+//   sign exactly at q = 1, so the minimum selects the right branch, and it is exactly 0 beyond q = 2.
+template <int SHAPE>
+__device__ __forceinline__ float shape_half_full(float s, const ShapeTab &tab)
+{
+    const float q = fast_sqrt(s);
+    if (SHAPE == SHAPE_CUBIC) {
+        const float p = fmaf(s, fmaf(0.375f, q, -0.75f), 0.5f);
+        const float a1 = __saturatef(fmaf(q, -0.5f, 1.0f));
+        return fminf(p, a1 * a1 * a1);
+    }
+    return shape_eval<SHAPE>(q, tab);
+}
+// cubic spline, outer annulus only (every q >= 1): f/2 = sat(1 - q/2)^3
+__device__ __forceinline__ float shape_half_outer(float s)
+{
+    const float a1 = __saturatef(fmaf(fast_sqrt(s), -0.5f, 1.0f));
+    return a1 * a1 * a1;
+}
 #endif
 
 }  // namespace ast

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
             const float qmin2 = ddx * ddx + ddy * ddy + ddz * ddz;
             hit = qmin2 < 4.0001f;
             outer = hit && SHAPE == SHAPE_CUBIC && qmin2 >= 1.0f;
-            P = make_float4(fx * sx, fy * sy, fz * sz, r.c);
+            P = make_float4(fx * sx, fy * sy, fz * sz, SHAPE == SHAPE_CUBIC ? 2.0f * r.c : r.c);   // cubic: loops return f/2
             S = make_float4(sx, sy, sz, 0.f);
         }
         const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
@@ -261,16 +261,16 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
             const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
             const float axy = fmaf(by2, by2, ax * ax);
             const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
-            acc[0] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c0, c0, axy)), a.tab), acc[0]);
-            acc[1] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c1, c1, axy)), a.tab), acc[1]);
-            acc[2] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c2, c2, axy)), a.tab), acc[2]);
-            acc[3] = fmaf(q.w, shape_eval<SHAPE>(fast_sqrt(fmaf(c3, c3, axy)), a.tab), acc[3]);
+            acc[0] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c0, c0, axy), a.tab), acc[0]);
+            acc[1] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c1, c1, axy), a.tab), acc[1]);
+            acc[2] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c2, c2, axy), a.tab), acc[2]);
+            acc[3] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c3, c3, axy), a.tab), acc[3]);
         }
         if (SHAPE == SHAPE_CUBIC) {
             for (int e = 32 - no; e < 32; ++e) {
                 const float4 s = sS[warp][e];
                 const float4 q = sP[warp][e];
-                const float cc = q.w + q.w;                       // the factor 2 of f = 2 a^3
+                const float cc = q.w;
                 const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
                 const float axy = fmaf(by2, by2, ax * ax);
                 const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);

@@ -367,7 +367,54 @@ struct Acc {
     double box_a, box_b;
     ShapeTab tab;
     size_t map_stride;
+    const uint32_t *seg_off;      // [ntiles + 1] exclusive scan of the segments per tile; seg_off[ntiles] = number of work items
+    uint32_t seg_target;          // target list entries per segment
+    int ntiles;
 };
+
+// K5b: work items.  A tile whose list is longer than seg_target entries is split into ceil(cnt / seg_target) balanced
+// segments, each accumulated by its own CTA (partial sums then go to the map with float64 atomics instead of a plain
+// read-modify-write).  This keeps every SM busy when few tiles hold most of the pairs: clustered particle sets, the slabs
+// that index-sharded ranks and host batches deposit, and the tail of the last wave.
+__device__ __forceinline__ uint32_t tile_segments(uint32_t cnt, uint32_t n_huge, uint32_t seg_target)
+{
+    if (cnt + n_huge == 0) return 0u;
+    return cnt <= seg_target ? 1u : (cnt + seg_target - 1) / seg_target;
+}
+__global__ void tile_segments_kernel(const uint32_t *__restrict__ tbeg, const uint32_t *__restrict__ tend, uint32_t n_huge,
+                                     uint32_t seg_target, int ntiles, uint32_t *__restrict__ seg_off)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    seg_off[t] = t < ntiles ? tile_segments(tend[t] - tbeg[t], n_huge, seg_target) : 0u;
+}
+
+struct TileWork {
+    int tile;
+    uint32_t beg, cnt, n_huge;
+    bool atomic_out;
+};
+// work item of this CTA (uniform over the CTA); false: nothing to do
+__device__ __forceinline__ bool resolve_work(const Acc &a, TileWork &w)
+{
+    const uint32_t b = blockIdx.x;
+    if (b >= a.seg_off[a.ntiles]) return false;
+    int lo = 0, hi = a.ntiles - 1;                 // first tile t with seg_off[t + 1] > b
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a.seg_off[mid + 1] > b) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t s0 = a.seg_off[lo], nseg = a.seg_off[lo + 1] - s0, seg = b - s0;
+    const uint32_t tb = a.tbeg[lo], cnt = a.tend[lo] - tb;
+    const uint32_t len = nseg > 1 ? (((cnt + nseg - 1) / nseg + 31u) & ~31u) : cnt;
+    const uint32_t off = seg * len;
+    w.tile = lo;
+    w.beg = tb + (off < cnt ? off : cnt);
+    w.cnt = off < cnt ? (cnt - off < len ? cnt - off : len) : 0u;
+    w.n_huge = seg == 0 ? a.n_huge : 0u;
+    w.atomic_out = nseg > 1;
+    return true;
+}
 
 // K6: the CTA maps to one 32x32 tile, but every warp walks the tile's list on its own for
 // its own sub-tile -- no CTA barrier anywhere.  Per 32 list entries: each lane stages one entry (float64 -> tile-relative
@@ -381,9 +428,11 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
     __shared__ float4 sP[NW][32];       // {ux*sx, uy*sy, sx, sy}
     __shared__ float2 sC[NW][32];       // {c0, c1}
 
-    const int tile = blockIdx.x;
-    const uint32_t beg = a.tbeg[tile], cnt = a.tend[tile] - beg;
-    const uint32_t total = cnt + a.n_huge;
+    TileWork w;
+    if (!resolve_work(a, w)) return;
+    const int tile = w.tile;
+    const uint32_t beg = w.beg, cnt = w.cnt;
+    const uint32_t total = cnt + w.n_huge;
     if (total == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tile / a.nty, ty = tile - tx * a.nty;
@@ -505,7 +554,8 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
-                *o += acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
+                const double v = acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
+                if (w.atomic_out) atomicAdd(o, v); else *o += v;
             }
         }
     }
@@ -527,32 +577,17 @@ struct __align__(16) RowColSlot {
 };
 static_assert(sizeof(RowColSlot) == 160, "slot layout");
 
-template <int SHAPE>
-__device__ __forceinline__ float shape_half_full(float s, const ShapeTab &tab)
-{
-    const float q = fast_sqrt(s);
-    if (SHAPE == SHAPE_CUBIC) {
-        const float p = fmaf(s, fmaf(0.375f, q, -0.75f), 0.5f);
-        const float a1 = __saturatef(fmaf(q, -0.5f, 1.0f));
-        return fminf(p, a1 * a1 * a1);
-    }
-    return shape_eval<SHAPE>(q, tab);
-}
-__device__ __forceinline__ float shape_half_outer(float s)
-{
-    const float a1 = __saturatef(fmaf(fast_sqrt(s), -0.5f, 1.0f));
-    return a1 * a1 * a1;
-}
-
 template <int SHAPE, int NP>
 __global__ void __launch_bounds__(256, 4) rowcol_accum_kernel(Acc a)
 {
     constexpr int NW = 8, WY = 2, SX = 8, SY = 16, PX = 2, PY = 2, LY = SY / PY, NPIX = PX * PY;
     __shared__ RowColSlot sS[NW][32];
 
-    const int tile = blockIdx.x;
-    const uint32_t beg = a.tbeg[tile], cnt = a.tend[tile] - beg;
-    const uint32_t total = cnt + a.n_huge;
+    TileWork w;
+    if (!resolve_work(a, w)) return;
+    const int tile = w.tile;
+    const uint32_t beg = w.beg, cnt = w.cnt;
+    const uint32_t total = cnt + w.n_huge;
     if (total == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tile / a.nty, ty = tile - tx * a.nty;
@@ -698,7 +733,8 @@ __global__ void __launch_bounds__(256, 4) rowcol_accum_kernel(Acc a)
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
-                *o += acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
+                const double v = acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
+                if (w.atomic_out) atomicAdd(o, v); else *o += v;
             }
         }
     }
@@ -760,7 +796,7 @@ struct Layout2 {
     uint64_t *scan_tmp;
     Rec *rec;
     uint64_t *pairs_a, *pairs_b, *huge;
-    uint32_t *tbeg, *tend;
+    uint32_t *tbeg, *tend, *seg_off, *seg_tmp;
     void *sort_ws;
     size_t bytes;
 };
@@ -802,6 +838,8 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.huge = c.take<uint64_t>(L.huge_cap);
     L.tbeg = c.take<uint32_t>(L.ntiles);
     L.tend = c.take<uint32_t>(L.ntiles);
+    L.seg_off = c.take<uint32_t>(L.ntiles + 1);
+    L.seg_tmp = c.take<uint32_t>(scan_num_blocks(L.ntiles + 1) + 2);
     L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
     L.bytes = c.bytes();
     return L;
@@ -1007,12 +1045,30 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
                 tile_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
                 st.n_launches += 1;
             }
-            tk.end();
             c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
+            // work items: balanced segments of the tile lists
+            {
+                static int sm_count = 0;
+                if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+                // enough items for ~4 waves of the resident CTA slots; AST_SEG_WAVES overrides (tuning knob)
+                static int waves = 0;
+                if (waves == 0) { const char *e = getenv("AST_SEG_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
+                const int64_t want_items = (int64_t)sm_count * 4 * waves;
+                int64_t target = (nw / want_items + 31) & ~(int64_t)31;
+                target = target < 1024 ? 1024 : (target > 65536 ? 65536 : target);
+                c.seg_off = L.seg_off; c.seg_target = (uint32_t)target; c.ntiles = (int)L.ntiles;
+                tile_segments_kernel<<<(unsigned)((L.ntiles + 1 + 255) / 256), 256, 0, s>>>(L.tbeg, L.tend, c.n_huge, c.seg_target,
+                                                                                        (int)L.ntiles, L.seg_off);
+                int nl = 0;
+                AST_CUDA_TRY(scan_exclusive<uint32_t>(L.seg_off, L.ntiles + 1, L.seg_tmp, nullptr, s, &nl));
+                st.n_launches += 1 + nl;
+            }
+            tk.end();
+            const int64_t max_items = L.ntiles + nw / (int64_t)c.seg_target;      // sum_t max(1, ceil(cnt_t / target)) <= this
             tk.begin(5);
-            if (a.shape == SHAPE_CUBIC) launch_accum<SHAPE_CUBIC>(p->n_prop, c, L.ntiles, s);
-            else if (a.shape == SHAPE_WENDLAND) launch_accum<SHAPE_WENDLAND>(p->n_prop, c, L.ntiles, s);
-            else launch_accum<SHAPE_TABLE>(p->n_prop, c, L.ntiles, s);
+            if (a.shape == SHAPE_CUBIC) launch_accum<SHAPE_CUBIC>(p->n_prop, c, max_items, s);
+            else if (a.shape == SHAPE_WENDLAND) launch_accum<SHAPE_WENDLAND>(p->n_prop, c, max_items, s);
+            else launch_accum<SHAPE_TABLE>(p->n_prop, c, max_items, s);
             tk.end();
             st.n_launches += 1;
             AST_CUDA_TRY(cudaGetLastError());

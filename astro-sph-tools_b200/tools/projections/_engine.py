@@ -130,10 +130,11 @@ class Projector2D:
 
     # ---- host call (numpy in, numpy out): what create_image uses -------------------------------------------
     def project_host(self, positions, smoothing_lengths, props, image_size, axis, bounds, kernel="cubic_spline_3d",
-                     periodic=False, box=None, stream=None, batch_particles=1 << 22, return_device=False):
+                     periodic=False, box=None, stream=None, batch_particles=1 << 22, return_device=False, ramp=True):
         """Host arrays in, host map out.  The particle arrays are streamed to the device in batches of
         `batch_particles` through two staging buffers on a copy stream, so the host-to-device transfer of batch b+1
         overlaps the deposition of batch b (deposition is linear in particles: batches accumulate into the same map).
+        With ramp=True the first batches are a quarter and a half of `batch_particles`, so the first (unhidden) copy is short.
         Pinned host arrays make the copies truly asynchronous; pageable ones still overlap with the running kernels."""
         torch = self.torch
         single = not isinstance(props, (list, tuple))
@@ -153,6 +154,14 @@ class Projector2D:
             smoothing_lengths = np.ascontiguousarray(smoothing_lengths)
             plist = [np.ascontiguousarray(q) for q in plist]
             bn = -(-n // nb)
+            # batch boundaries: [bn/4, bn/2, bn, bn, ...] when ramping (the copy of batch b+1 stays shorter than the work on b)
+            cuts = [0]
+            if ramp and nb >= 2:
+                for frac in (4, 2):
+                    cuts.append(min(n, cuts[-1] + max(1, bn // frac)))
+            while cuts[-1] < n:
+                cuts.append(min(n, cuts[-1] + bn))
+            nb = len(cuts) - 1
             with torch.cuda.device(dev):
                 compute = stream if stream is not None else torch.cuda.current_stream()
                 if getattr(self, "_copy_stream", None) is None:
@@ -170,7 +179,7 @@ class Projector2D:
                 copy.wait_stream(compute)
                 n_launch = 0
                 for b in range(nb):
-                    lo, hi = b * bn, min(n, (b + 1) * bn)
+                    lo, hi = cuts[b], cuts[b + 1]
                     m = hi - lo
                     if m <= 0:
                         break

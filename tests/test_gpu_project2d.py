@@ -167,7 +167,10 @@ def test_batched_host_pipeline_matches_single_batch(oracle):
     ref = oracle.project2d(pos, h, np.stack([prop, 2 * prop]), (80, 80), 2, 0.0, 10.0, 0.0, 10.0)
     eng = Projector2D()
     one = eng.project_host(pos, h, [prop, 2 * prop], (80, 80), 2, (0.0, 10.0, 0.0, 10.0))
-    many = eng.project_host(pos, h, [prop, 2 * prop], (80, 80), 2, (0.0, 10.0, 0.0, 10.0), batch_particles=1000)
+    ramped = eng.project_host(pos, h, [prop, 2 * prop], (80, 80), 2, (0.0, 10.0, 0.0, 10.0), batch_particles=1000)
+    assert eng.last_stats["n_batches"] == 10            # 219 + 438 particles first, then batches of 876
+    assert rel_l2(ramped, ref) <= 1e-5
+    many = eng.project_host(pos, h, [prop, 2 * prop], (80, 80), 2, (0.0, 10.0, 0.0, 10.0), batch_particles=1000, ramp=False)
     assert eng.last_stats["n_batches"] == 8
     check(one[0], ref[0]); check(many[1], ref[1])
     assert rel_l2(many, one) < 1e-7           # only the float32 partial-sum grouping differs between batchings
