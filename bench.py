@@ -71,7 +71,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -82,17 +82,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """number of samples read so far (brackets the timed region)"""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        # samples taken between the two marks (the timed region); if the region was shorter than nvidia-smi's period, the
+        # samples of the identical warm-up steps just before it
+        window = self.lines[first:(last if last is not None else len(self.lines)) + 1]
+        if not window:
+            window = self.lines[max(0, first - 4):first + 1]
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -246,24 +255,34 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
     launches_per_step = eng.last_stats["n_launches"]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    if rank == 0:                     # nvidia-smi needs a few hundred ms to deliver its first sample: keep the GPU under the
+        t_wait = time.time()          # same load (extra untimed warm-up steps) until it has
+        while sampler.proc is not None and sampler.mark() == 0 and time.time() - t_wait < 3.0:
+            if world == 1:
+                step()
+                torch.cuda.synchronize()
+            else:                     # step() holds a collective: rank 0 must not run it alone
+                time.sleep(0.02)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    m0 = sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     sync_all()
+    m1 = sampler.mark()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(m0, m1) if rank == 0 else None
     ms_per_step = float(ms.item()) / args.steps
     value = world * N / (ms_per_step * 1e-3)
 
