@@ -34,6 +34,8 @@ struct KnnArgs {
     const uint32_t *qlist;       // nullable: sorted positions of the queries
     const double *qpos;          // EXTERNAL queries: (nq,3) row-major positions, output row = query index
     int64_t nq, q_begin;
+    const uint32_t *col_off;     // [G*G + 1] exclusive scan of the 32-query chunks per (cx, cy) column (warp-cooperative kernel)
+    int64_t q_end;               // queries = particles with original index in [q_begin, q_end)
     int k;
     double *h_out;
     int32_t *idx_out;
@@ -232,12 +234,287 @@ __global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
     }
 }
 
+
+// ---- warp-cooperative queries ---------------------------------------------------------------------------------------
+// One warp answers 32 consecutive particles of one (cx, cy) column of cells (a run of cells along z, contiguous in the
+// cell-ordered arrays).  All 32 queries walk the SAME candidates: for every ring the warp visits the new columns
+// (cx + ox, cy + oy) over the z-range [zlo - ring, zhi + ring] of the chunk and the two new z-caps of the columns it already
+// knows; each piece is one contiguous particle range (prefix cstart), loaded 32 candidates at a time into shared memory by
+// the whole warp (coalesced) and then read by every lane as a broadcast.  No divergence in the distance loop, candidate
+// loads shared by 32 queries; only the heap insert is per lane.  The thread-per-query kernel above evaluates ~250 candidates
+// per query on 16 of 32 lanes and stalls on scattered gathers; this one evaluates ~860 per query in lock step (23 SASS
+// instructions each) and, as measured, spends as many instructions again in the lock-step heap merges (ncu: 3.5e10 warp
+// instructions, 80 ms at 256^3 against 2.8e10 and 46 ms), so it is NOT the default; it is kept, tested bit-equal to scipy,
+// as the starting point for a selection scheme that does not pay a sift-down per accepted candidate.
+// Arithmetic is scipy's, pair by pair: d2 = (ex*ex + ey*ey) + ez*ez with each delta wrapped by -+box when |delta| > box/2.
+// When every pair of (chunk, candidate piece) provably takes the same wrap branch on an axis (cell offsets at least one cell
+// away from box/2: 2 (|offset| + 2) <= G) the wrap is a per-piece constant shift added to the delta -- the same operation
+// the branch would have performed -- otherwise the per-pair comparison is kept.
+__global__ void knn_col_chunks_kernel(const uint32_t *__restrict__ cstart, int G, uint32_t *__restrict__ col_off)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col > G * G) return;
+    col_off[col] = col < G * G ? (cstart[(int64_t)col * G + G] - cstart[(int64_t)col * G] + 31u) / 32u : 0u;
+}
+
+// number of chunks with at least one query of the subset [q_begin, q_end) (decides between the two query kernels)
+__global__ void knn_active_chunks_kernel(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ col_off,
+                                         const uint32_t *__restrict__ sidx, int G, int64_t q_begin, int64_t q_end,
+                                         unsigned long long *__restrict__ count)
+{
+    const int col = blockIdx.x;
+    const uint32_t b = cstart[(int64_t)col * G], e = cstart[(int64_t)col * G + G];
+    unsigned long long mine = 0;
+    for (uint32_t c = b + 32u * threadIdx.x; c < e; c += 32u * blockDim.x) {
+        bool any = false;
+        for (uint32_t j = c; j < e && j < c + 32u; ++j) any = any || ((int64_t)sidx[j] >= q_begin && (int64_t)sidx[j] < q_end);
+        mine += any ? 1ull : 0ull;
+    }
+    if (mine) atomicAdd(count, mine);
+}
+
+// max-heap in SHARED memory, entry i of lane l at [i * 32 + l] (conflict-free); see knn_block_kernel
+template <bool WANT_IDX>
+struct SHeap {
+    double *d;          // already offset by the lane
+    uint32_t *id;
+    int k;
+    __device__ __forceinline__ double &D(int i) const { return d[i * 32]; }
+    __device__ __forceinline__ uint32_t &I(int i) const { return id[i * 32]; }
+    __device__ __forceinline__ bool less(double d2, uint32_t j, double e2, uint32_t l) const
+    {
+        return WANT_IDX ? (d2 < e2 || (d2 == e2 && j < l)) : (d2 < e2);
+    }
+    __device__ __forceinline__ void replace_root(double d2, uint32_t j)
+    {
+        int p = 0;
+        for (;;) {
+            int c = 2 * p + 1;
+            if (c >= k) break;
+            double dc = D(c);
+            uint32_t ic = WANT_IDX ? I(c) : 0u;
+            if (c + 1 < k) {
+                const double dr = D(c + 1);
+                const uint32_t ir = WANT_IDX ? I(c + 1) : 0u;
+                if (less(dc, ic, dr, ir)) { ++c; dc = dr; ic = ir; }
+            }
+            if (!less(d2, j, dc, ic)) break;
+            D(p) = dc;
+            if (WANT_IDX) I(p) = ic;
+            p = c;
+        }
+        D(p) = d2;
+        if (WANT_IDX) I(p) = j;
+    }
+};
+
+constexpr int kPend = 16;          // pending-list slots per lane (flush when a lane holds more than kPend - 8)
+__host__ __device__ inline size_t knn_block_warp_bytes(int k, bool want_idx)
+{
+    return (size_t)(k + kPend + 3) * 32 * sizeof(double) + (want_idx ? (size_t)(k + kPend + 1) * 32 * sizeof(uint32_t) : 0);
+}
+
+template <int WARPS, bool WANT_IDX, bool PER>
+__global__ void __launch_bounds__(WARPS * 32) knn_block_kernel(KnnArgs a)
+{
+    // per warp: heap [k][32] doubles, pending [kPend][32], candidates x, y, z [32]; then (lists) the matching uint32 indices
+    extern __shared__ __align__(16) unsigned char knn_smem[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *const wd = reinterpret_cast<double *>(knn_smem + (size_t)wib * knn_block_warp_bytes(a.k, WANT_IDX));
+    double *const pend = wd + (size_t)a.k * 32 + lane;                    // pend[t * 32]
+    double *const sx = wd + (size_t)(a.k + kPend) * 32, *const sy = sx + 32, *const sz = sy + 32;
+    uint32_t *const wi = reinterpret_cast<uint32_t *>(sz + 32);
+    uint32_t *const pend_id = wi + (size_t)a.k * 32 + lane;
+    uint32_t *const si = wi + (size_t)(a.k + kPend) * 32;
+    const uint32_t w = blockIdx.x * (uint32_t)WARPS + (uint32_t)wib;      // chunk index
+    const KnnGrid &g = a.g;
+    const int G = g.G, ncol = G * G;
+    if (w >= a.col_off[ncol]) return;
+    int lo = 0, hi = ncol - 1;                                            // first column with col_off[col + 1] > w
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a.col_off[mid + 1] > w) hi = mid; else lo = mid + 1;
+    }
+    const int col = lo, cx = col / G, cy = col - cx * G;
+    const uint32_t cend = a.cstart[(int64_t)col * G + G];
+    const uint32_t s0 = a.cstart[(int64_t)col * G] + 32u * (w - a.col_off[col]);
+    const uint32_t s = s0 + (uint32_t)lane < cend ? s0 + (uint32_t)lane : s0;      // lanes past the end shadow the first query
+    const uint32_t oi = a.sidx[s];
+    const bool active = s0 + (uint32_t)lane < cend && (int64_t)oi >= a.q_begin && (int64_t)oi < a.q_end;
+    if (!__any_sync(FULL, active)) return;
+    const double x = a.xs[s], y = a.ys[s], z = a.zs[s];
+    const int qc[3] = { cx, cy, cell_coord(g, z, 2) };
+    const double xq[3] = { x, y, z };
+    const int zlo = __reduce_min_sync(FULL, active ? qc[2] : G), zhi = __reduce_max_sync(FULL, active ? qc[2] : -1);
+    const int zspan = zhi - zlo;
+
+    SHeap<WANT_IDX> hp;
+    hp.k = a.k;
+    hp.d = wd + lane;
+    hp.id = wi + lane;
+    for (int i = 0; i < a.k; ++i) {
+        hp.D(i) = INFINITY;
+        if (WANT_IDX) hp.I(i) = 0xffffffffu;
+    }
+    double kth = active ? INFINITY : -INFINITY;                           // inactive lanes never accept a candidate
+
+    // Selection in lock step: a candidate that beats the lane's current K-th distance is only APPENDED to a small per-lane
+    // pending list (predicated store, no branch); the lists are merged into the heaps by all lanes together when one of them
+    // could overflow with the next 32 candidates, and before every termination test.  Inserting straight into the heap would
+    // run the divergent sift-down for almost every candidate (some lane of the 32 nearly always accepts).
+    int cnt = 0;
+    auto offer = [&](double d2, uint32_t oj) {
+        if (WANT_IDX ? d2 <= kth : d2 < kth) {
+            pend[cnt * 32] = d2;
+            if (WANT_IDX) pend_id[cnt * 32] = oj;
+            ++cnt;
+        }
+    };
+    auto flush = [&]() {
+        const int mx = __reduce_max_sync(FULL, cnt);
+        for (int t = 0; t < mx; ++t) {
+            if (t < cnt) {
+                const double d2 = pend[t * 32];
+                const uint32_t oj = WANT_IDX ? pend_id[t * 32] : 0u;
+                if (hp.less(d2, oj, hp.D(0), WANT_IDX ? hp.I(0) : 0u)) hp.replace_root(d2, oj);
+            }
+        }
+        cnt = 0;
+        kth = active ? hp.D(0) : -INFINITY;
+    };
+    // candidates [jb, je): simple = the wrap of every pair is the constant shift (shx, shy, shz)
+    auto scan_range = [&](uint32_t jb, uint32_t je, bool simple, double shx, double shy, double shz) {
+        for (uint32_t j0 = jb; j0 < je; j0 += 32u) {
+            const uint32_t j = j0 + (uint32_t)lane;
+            __syncwarp();
+            if (j < je) {
+                sx[lane] = a.xs[j]; sy[lane] = a.ys[j]; sz[lane] = a.zs[j];
+                if (WANT_IDX) si[lane] = a.sidx[j];
+            }
+            __syncwarp();
+            const int m = (int)(je - j0 < 32u ? je - j0 : 32u);
+            for (int t0 = 0; t0 < m; t0 += 8) {                            // at most 8 appends per lane between two flush tests
+                const int t1 = min(t0 + 8, m);
+                if (!PER || simple) {
+                    for (int t = t0; t < t1; ++t) {
+                        double ex = sx[t] - x, ey = sy[t] - y, ez = sz[t] - z;
+                        if (PER) { ex = AST_DADD(ex, shx); ey = AST_DADD(ey, shy); ez = AST_DADD(ez, shz); }
+                        offer(AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez)), WANT_IDX ? si[t] : 0u);
+                    }
+                } else {
+                    for (int t = t0; t < t1; ++t) {
+                        double ex = sx[t] - x, ey = sy[t] - y, ez = sz[t] - z;
+                        if (ex < -g.half_box) ex += g.box; else if (ex > g.half_box) ex -= g.box;
+                        if (ey < -g.half_box) ey += g.box; else if (ey > g.half_box) ey -= g.box;
+                        if (ez < -g.half_box) ez += g.box; else if (ez > g.half_box) ez -= g.box;
+                        offer(AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez)), WANT_IDX ? si[t] : 0u);
+                    }
+                }
+                if (__any_sync(FULL, cnt > kPend - 8)) flush();
+            }
+        }
+    };
+    // raw z-cells [z0, z1] (may stick out of [0, G)) of column (ccx, ccy); at most G cells
+    auto scan_z = [&](int ccx, int ccy, int z0, int z1, bool simple_xy, double shx, double shy, int ring) {
+        const uint32_t base = ((uint32_t)ccx * G + ccy) * G;
+        if (!PER) {
+            z0 = max(z0, 0); z1 = min(z1, G - 1);
+            if (z0 <= z1) scan_range(a.cstart[base + z0], a.cstart[base + z1 + 1], true, 0.0, 0.0, 0.0);
+            return;
+        }
+        const bool simple = simple_xy && 2 * (zspan + ring + 2) <= G;
+        if (z1 - z0 + 1 >= G) { scan_range(a.cstart[base], a.cstart[base + G], false, 0.0, 0.0, 0.0); return; }
+        if (z0 < 0) {
+            // cells z0+G .. min(z1,-1)+G lie above the chunk after wrapping: raw delta ~ +box -> the pair subtracts box
+            const int zt = min(z1, -1);
+            scan_range(a.cstart[base + z0 + G], a.cstart[base + zt + G + 1], simple, shx, shy, -g.box);
+            if (z1 >= 0) scan_range(a.cstart[base], a.cstart[base + z1 + 1], simple, shx, shy, 0.0);
+        } else if (z1 >= G) {
+            const int zb = max(z0, G);
+            if (z0 < G) scan_range(a.cstart[base + z0], a.cstart[base + G], simple, shx, shy, 0.0);
+            scan_range(a.cstart[base + zb - G], a.cstart[base + z1 - G + 1], simple, shx, shy, g.box);
+        } else {
+            scan_range(a.cstart[base + z0], a.cstart[base + z1 + 1], simple, shx, shy, 0.0);
+        }
+    };
+
+    for (int ring = 0;; ++ring) {
+        const int len_prev = zspan + 1 + 2 * (ring - 1);                  // z-cells of a known column before this ring
+        for (int ox = -ring; ox <= ring; ++ox) {
+            int ccx = cx + ox;
+            double shx = 0.0;
+            if (PER) {
+                if (2 * abs(ox) > G || (2 * abs(ox) == G && ox < 0)) continue;
+                if (ccx < 0) { ccx += G; shx = -g.box; } else if (ccx >= G) { ccx -= G; shx = g.box; }
+            } else if (ccx < 0 || ccx >= G) continue;
+            for (int oy = -ring; oy <= ring; ++oy) {
+                int ccy = cy + oy;
+                double shy = 0.0;
+                if (PER) {
+                    if (2 * abs(oy) > G || (2 * abs(oy) == G && oy < 0)) continue;
+                    if (ccy < 0) { ccy += G; shy = -g.box; } else if (ccy >= G) { ccy -= G; shy = g.box; }
+                } else if (ccy < 0 || ccy >= G) continue;
+                const bool simple_xy = 2 * (abs(ox) + 2) <= G && 2 * (abs(oy) + 2) <= G;
+                if (abs(ox) == ring || abs(oy) == ring) {
+                    scan_z(ccx, ccy, zlo - ring, zhi + ring, simple_xy, shx, shy, ring);          // new column: whole z-range
+                } else if (!PER) {
+                    scan_z(ccx, ccy, zlo - ring, zlo - ring, simple_xy, shx, shy, ring);          // known column: the two new caps
+                    scan_z(ccx, ccy, zhi + ring, zhi + ring, simple_xy, shx, shy, ring);
+                } else {
+                    // periodic: a cap is new only while the known z-range has not closed on itself
+                    if (len_prev + 1 <= G) scan_z(ccx, ccy, zlo - ring, zlo - ring, simple_xy, shx, shy, ring);
+                    if (len_prev + 2 <= G) scan_z(ccx, ccy, zhi + ring, zhi + ring, simple_xy, shx, shy, ring);
+                }
+            }
+        }
+        flush();
+        // per lane: smallest possible distance to anything outside the cube of cells explored around ITS OWN cell (the
+        // warp has explored a superset of it)
+        double dmin = INFINITY;
+        bool all = true;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double frac = xq[c] - (g.lo[c] + (double)qc[c] * g.cs[c]);
+            bool lo_open, hi_open;
+            if (PER) lo_open = hi_open = (2 * ring + 1 < G);
+            else { lo_open = qc[c] - ring > 0; hi_open = qc[c] + ring < G - 1; }
+            if (lo_open) dmin = fmin(dmin, frac + (double)ring * g.cs[c]);
+            if (hi_open) dmin = fmin(dmin, (g.cs[c] - frac) + (double)ring * g.cs[c]);
+            all = all && !lo_open && !hi_open;
+        }
+        const double safe = dmin - 1e-9 * g.cs[0];
+        const bool done = !active || all || (safe > 0.0 && kth < safe * safe);
+        if (__all_sync(FULL, done)) break;
+    }
+    if (!active) return;
+    const int64_t row = (int64_t)oi - a.q_begin;
+    if (a.h_out) a.h_out[row] = sqrt(hp.D(0));
+    if (WANT_IDX) {
+        const int k = a.k;
+        for (int end = k - 1; end > 0; --end) {                 // heap-sort in place: ascending (d2, idx)
+            const double dd = hp.D(end);
+            const uint32_t ii = hp.I(end);
+            hp.D(end) = hp.D(0);
+            hp.I(end) = hp.I(0);
+            hp.k = end;
+            hp.replace_root(dd, ii);
+        }
+        for (int i = 0; i < k; ++i) {
+            if (a.idx_out) a.idx_out[row * k + i] = hp.D(i) < INFINITY ? (int32_t)hp.I(i) : -1;
+            if (a.dist_out) a.dist_out[row * k + i] = sqrt(hp.D(i));
+        }
+    }
+}
+
 struct KnnLayout {
     int G;
     int64_t ncell, nq;
     uint64_t *ea, *eb;
     double *xs, *ys, *zs;
     uint32_t *sidx, *cbeg, *qflag, *qlist, *scan_tmp, *cell_tmp;   // cbeg: ncell + 1 counts -> exclusive scan = cstart
+    uint32_t *col_off;                                             // G*G + 1 chunk offsets (warp-cooperative kernel)
+    unsigned long long *active_chunks;
     void *sort_ws;
     size_t bytes;
 };
@@ -273,6 +550,8 @@ static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
     L.sidx = c.take<uint32_t>(n);
     L.cbeg = c.take<uint32_t>(L.ncell + 1);
     L.cell_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(L.ncell + 1));
+    L.col_off = c.take<uint32_t>((int64_t)L.G * L.G + 1);
+    L.active_chunks = c.take<unsigned long long>(1);
     L.qflag = c.take<uint32_t>(n);
     L.qlist = c.take<uint32_t>(n);
     L.scan_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(n));
@@ -288,6 +567,29 @@ static void launch_query(const KnnArgs &a, bool want_idx, cudaStream_t s)
     if (a.qpos) knn_query_kernel<KCAP, true, true><<<nb, 128, 0, s>>>(a);
     else if (want_idx) knn_query_kernel<KCAP, true, false><<<nb, 128, 0, s>>>(a);
     else knn_query_kernel<KCAP, false, false><<<nb, 128, 0, s>>>(a);
+}
+
+template <int WARPS, bool WANT_IDX, bool PER>
+static cudaError_t launch_block_t(const KnnArgs &a, int64_t n, cudaStream_t s)
+{
+    const size_t smem = WARPS * knn_block_warp_bytes(a.k, WANT_IDX);
+    cudaError_t e = cudaFuncSetAttribute(knn_block_kernel<WARPS, WANT_IDX, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t max_chunks = n / 32 + (int64_t)a.g.G * a.g.G;          // sum over columns of ceil(count / 32) <= this
+    knn_block_kernel<WARPS, WANT_IDX, PER><<<(unsigned)((max_chunks + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+template <int WARPS>
+static cudaError_t launch_block_w(const KnnArgs &a, bool want_idx, int64_t n, cudaStream_t s)
+{
+    const bool per = a.g.box > 0.0;
+    if (want_idx) return per ? launch_block_t<WARPS, true, true>(a, n, s) : launch_block_t<WARPS, true, false>(a, n, s);
+    return per ? launch_block_t<WARPS, false, true>(a, n, s) : launch_block_t<WARPS, false, false>(a, n, s);
+}
+// warps per block by k: the shared-memory heaps ((k + 19) * 256 bytes per warp, 1.5x with lists) should leave >= 3 blocks per SM
+static cudaError_t launch_block(const KnnArgs &a, bool want_idx, int64_t n, cudaStream_t s)
+{
+    return a.k <= 64 ? launch_block_w<4>(a, want_idx, n, s) : launch_block_w<2>(a, want_idx, n, s);
 }
 
 // builds the cell list of `pos` in the workspace (steps 1 and 2) and fills the grid / array part of KnnArgs
@@ -363,12 +665,36 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
     if (rc) return rc;
     a.nq = q_end - q_begin;
     a.q_begin = q_begin;
+    a.q_end = q_end;
     a.h_out = h_out; a.idx_out = idx_out; a.dist_out = dist_out;
     const bool want = idx_out != nullptr || dist_out != nullptr;
-    if (p->k <= 32) launch_query<32>(a, want, s);
-    else if (p->k <= 48) launch_query<48>(a, want, s);
-    else if (p->k <= 64) launch_query<64>(a, want, s);
-    else launch_query<128>(a, want, s);
+    // warp-cooperative kernel (opt-in, AST_KNN_WARP_COOPERATIVE): 32 consecutive particles of a column of cells per warp.
+    // Measured on B200 (256^3, k = 48): 80 ms against 46 ms for one thread per query -- see the note in DESIGN.md section 7.
+    // With a query subset it only makes sense if the subset is spatially coherent (index ranges of snapshot files are):
+    // count the chunks that hold at least one query and fall back when more than 3x the ideal number would have to run.
+    bool cooperative = (p->flags & AST_KNN_WARP_COOPERATIVE) != 0;
+    if (cooperative) {
+        const int ncol = L.G * L.G;
+        knn_col_chunks_kernel<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, s>>>(L.cbeg, L.G, L.col_off);
+        AST_CUDA_TRY(scan_exclusive<uint32_t>(L.col_off, (int64_t)ncol + 1, L.cell_tmp, nullptr, s));
+        a.col_off = L.col_off;
+        if (subset) {
+            unsigned long long active = 0;
+            AST_CUDA_TRY(cudaMemsetAsync(L.active_chunks, 0, sizeof(unsigned long long), s));
+            knn_active_chunks_kernel<<<(unsigned)ncol, 32, 0, s>>>(L.cbeg, L.col_off, L.sidx, L.G, q_begin, q_end, L.active_chunks);
+            AST_CUDA_TRY(cudaMemcpyAsync(&active, L.active_chunks, sizeof active, cudaMemcpyDeviceToHost, s));
+            AST_CUDA_TRY(cudaStreamSynchronize(s));
+            cooperative = (int64_t)active * 32 <= 3 * a.nq + 3 * 32;
+        }
+    }
+    if (cooperative) {
+        AST_CUDA_TRY(launch_block(a, want, n, s));
+    } else {
+        if (p->k <= 32) launch_query<32>(a, want, s);
+        else if (p->k <= 48) launch_query<48>(a, want, s);
+        else if (p->k <= 64) launch_query<64>(a, want, s);
+        else launch_query<128>(a, want, s);
+    }
     AST_CUDA_TRY(cudaGetLastError());
     return AST_OK;
 }
@@ -395,6 +721,8 @@ extern "C" int ast_knn_query(const ast_knn_params *p, const double *data_pos, co
     a.qpos = query_pos;
     a.nq = n_query;
     a.q_begin = 0;
+    a.q_end = p->n;
+    a.col_off = nullptr;
     a.h_out = nullptr; a.idx_out = idx_out; a.dist_out = dist_out;
     if (p->k <= 32) launch_query<32>(a, true, s);
     else if (p->k <= 48) launch_query<48>(a, true, s);
