@@ -99,17 +99,28 @@ struct Heap {
     {
         return WANT_IDX ? (d2 < e2 || (d2 == e2 && j < l)) : (d2 < e2);
     }
+    // 4-ary heap: children of p are 4p+1 .. 4p+4.  Three levels instead of six at k = 48, and the four child loads of a
+    // level are independent (the binary version waited for two dependent local-memory loads per level: 46 % of all
+    // stall samples of the query kernel, profiles/r01_v4_summary.md)
     __device__ __forceinline__ void replace_root(double d2, uint32_t j)
     {
         int p = 0;
         for (;;) {
-            int c = 2 * p + 1;
+            const int c = 4 * p + 1;
             if (c >= k) break;
-            if (c + 1 < k && less(d[c], WANT_IDX ? id[c] : 0u, d[c + 1], WANT_IDX ? id[c + 1] : 0u)) ++c;   // larger child
-            if (!less(d2, j, d[c], WANT_IDX ? id[c] : 0u)) break;
-            d[p] = d[c];
-            if (WANT_IDX) id[p] = id[c];
-            p = c;
+            const int c1 = min(c + 1, k - 1), c2 = min(c + 2, k - 1), c3 = min(c + 3, k - 1);      // clamped: re-reads the last child
+            const double e0 = d[c], e1 = d[c1], e2 = d[c2], e3 = d[c3];
+            const uint32_t i0 = WANT_IDX ? id[c] : 0u, i1 = WANT_IDX ? id[c1] : 0u, i2 = WANT_IDX ? id[c2] : 0u, i3 = WANT_IDX ? id[c3] : 0u;
+            int ma = c, mb = c2;
+            double da = e0, db = e2;
+            uint32_t ia = i0, ib = i2;
+            if (less(e0, i0, e1, i1)) { ma = c1; da = e1; ia = i1; }
+            if (less(e2, i2, e3, i3)) { mb = c3; db = e3; ib = i3; }
+            if (less(da, ia, db, ib)) { ma = mb; da = db; ia = ib; }                                // largest child
+            if (!less(d2, j, da, ia)) break;
+            d[p] = da;
+            if (WANT_IDX) id[p] = ia;
+            p = ma;
         }
         d[p] = d2;
         if (WANT_IDX) id[p] = j;
@@ -285,23 +296,25 @@ struct SHeap {
     {
         return WANT_IDX ? (d2 < e2 || (d2 == e2 && j < l)) : (d2 < e2);
     }
-    __device__ __forceinline__ void replace_root(double d2, uint32_t j)
+    __device__ __forceinline__ void replace_root(double d2, uint32_t j)      // 4-ary, as Heap::replace_root
     {
         int p = 0;
         for (;;) {
-            int c = 2 * p + 1;
+            const int c = 4 * p + 1;
             if (c >= k) break;
-            double dc = D(c);
-            uint32_t ic = WANT_IDX ? I(c) : 0u;
-            if (c + 1 < k) {
-                const double dr = D(c + 1);
-                const uint32_t ir = WANT_IDX ? I(c + 1) : 0u;
-                if (less(dc, ic, dr, ir)) { ++c; dc = dr; ic = ir; }
-            }
-            if (!less(d2, j, dc, ic)) break;
-            D(p) = dc;
-            if (WANT_IDX) I(p) = ic;
-            p = c;
+            const int c1 = min(c + 1, k - 1), c2 = min(c + 2, k - 1), c3 = min(c + 3, k - 1);
+            const double e0 = D(c), e1 = D(c1), e2 = D(c2), e3 = D(c3);
+            const uint32_t i0 = WANT_IDX ? I(c) : 0u, i1 = WANT_IDX ? I(c1) : 0u, i2 = WANT_IDX ? I(c2) : 0u, i3 = WANT_IDX ? I(c3) : 0u;
+            int ma = c, mb = c2;
+            double da = e0, db = e2;
+            uint32_t ia = i0, ib = i2;
+            if (less(e0, i0, e1, i1)) { ma = c1; da = e1; ia = i1; }
+            if (less(e2, i2, e3, i3)) { mb = c3; db = e3; ib = i3; }
+            if (less(da, ia, db, ib)) { ma = mb; da = db; ia = ib; }
+            if (!less(d2, j, da, ia)) break;
+            D(p) = da;
+            if (WANT_IDX) I(p) = ia;
+            p = ma;
         }
         D(p) = d2;
         if (WANT_IDX) I(p) = j;
