@@ -39,6 +39,9 @@ struct P3 {
     double norm_c;
     int norm_dim;
     int64_t small_max_vox, huge_min_bricks;
+    // written by bin3_kernel for the blocks that have pairs or large-h entries, read by emit3_kernel (one enumeration there)
+    uint32_t *pcount;                // pairs of particle i
+    uint64_t *pmask;                 // bit m: image m is tiled, bit 27 + m: image m is on the large-h list
 };
 
 
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
     __shared__ uint32_t red[34];
     const int64_t i = (int64_t)blockIdx.x * kBin3Threads + threadIdx.x;
     uint32_t npairs = 0, nhuge = 0;
+    uint64_t mask = 0;
     if (i < p.n) {
         const double x0[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
         const double h = p.h[i], R2 = radius2(h), h2 = 2.0 * h;
@@ -95,9 +99,11 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
                 if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * norm3(p, h));
             } else if (b.cls == CLS_TILED) {
                 npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
+                mask |= 1ull << m;
                 need_rec = true;
             } else if (b.cls == CLS_HUGE) {
                 ++nhuge;
+                mask |= 1ull << (27 + m);
                 need_rec = true;
             }
         }
@@ -111,6 +117,7 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
     }
     uint32_t tp = block_sum_u32(npairs, red);
     uint32_t th = block_sum_u32(nhuge, red);
+    if ((tp | th) != 0u && i < p.n) { p.pcount[i] = npairs; p.pmask[i] = mask; }     // emit3 only visits blocks with entries
     if (threadIdx.x == 0) {
         block_pairs[blockIdx.x] = tp;
         block_huge[blockIdx.x] = th;
@@ -129,28 +136,23 @@ __global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_
     const bool any_huge = write_huge && hnext > hbase;
     if (!any_pairs && !any_huge) return;
     const int64_t i = (int64_t)blockIdx.x * kBin3Threads + threadIdx.x;
-    double x0[3] = { 0, 0, 0 }, h = 0, R2 = 0, h2 = 0;
+    // counts and image masks come from bin3_kernel: one enumeration of the bricks here, and only for the images that have any
     uint32_t npairs = 0, nhuge = 0;
+    uint64_t mask = 0;
     if (i < p.n) {
-        x0[0] = p.pos[3 * i]; x0[1] = p.pos[3 * i + 1]; x0[2] = p.pos[3 * i + 2];
-        h = p.h[i];
-        R2 = radius2(h);
-        h2 = 2.0 * h;
-        for (int m = 0; m < p.n_img; ++m) {
-            const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
-            if (!may_touch(p.ax[0], q[0], h2) || !may_touch(p.ax[1], q[1], h2) || !may_touch(p.ax[2], q[2], h2)) continue;
-            Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
-            if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
-            else if (b.cls == CLS_HUGE) ++nhuge;
-        }
+        npairs = p.pcount[i];
+        mask = p.pmask[i];
+        nhuge = (uint32_t)__popcll(mask >> 27);
     }
     uint32_t tot;
     uint64_t g = pbase + block_excl_scan_u32(npairs, sm, &tot);
     uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
     if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
+    const double x0[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
+    const double h = p.h[i], R2 = radius2(h);
     for (int m = 0; m < p.n_img; ++m) {
+        if (!((mask >> m) & 0x8000001ull)) continue;                       // image m has neither pairs nor a large-h entry
         const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
-        if (!may_touch(p.ax[0], q[0], h2) || !may_touch(p.ax[1], q[1], h2) || !may_touch(p.ax[2], q[2], h2)) continue;
         Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
         if (b.cls == CLS_TILED) {
             for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [&](uint32_t key) {
@@ -324,6 +326,8 @@ struct Layout3 {
     int64_t nb, nbricks, pair_cap, huge_cap;
     uint64_t *block_pairs, *block_huge;
     Rec3 *rec;
+    uint32_t *pcount;
+    uint64_t *pmask;
     uint64_t *pairs_a, *pairs_b, *huge;
     uint32_t *tbeg, *tend;
     void *sort_ws;
@@ -361,6 +365,8 @@ static Layout3 layout3(const ast_grid3d_params *p, void *ws)
     L.block_pairs = c.take<uint64_t>(L.nb + 1);
     L.block_huge = c.take<uint64_t>(L.nb + 1);
     L.rec = c.take<Rec3>(p->n > 0 ? p->n : 1);
+    L.pcount = c.take<uint32_t>(p->n > 0 ? p->n : 1);
+    L.pmask = c.take<uint64_t>(p->n > 0 ? p->n : 1);
     L.pairs_a = c.take<uint64_t>(L.pair_cap);
     L.pairs_b = c.take<uint64_t>(L.pair_cap);
     L.huge = c.take<uint64_t>(L.huge_cap);
@@ -428,6 +434,7 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
     ast_project2d_stats st;
     memset(&st, 0, sizeof st);
     P3 a = make_p3(p, pos, h, prop, out);
+    a.pcount = L.pcount; a.pmask = L.pmask;
     const size_t nvox = (size_t)p->nx * p->ny * p->nz;
     tm.begin(7);
     tk.begin(6);
@@ -526,6 +533,7 @@ extern "C" int ast_bin3d(const ast_grid3d_params *p, const double *pos, const do
     }
     cudaStream_t s = (cudaStream_t)stream;
     P3 a = make_p3(p, pos, h, nullptr, nullptr);
+    a.pcount = L.pcount; a.pmask = L.pmask;
     uint64_t totals[2] = { 0, 0 };
     AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));

@@ -53,6 +53,9 @@ struct P2 {
     double box_a, box_b;                // periodic image m = 3*(ia+1) + (ib+1), shift = (ia*box_a, ib*box_b)
     int64_t small_max_px, huge_min_tiles;
     size_t map_stride;
+    // written by K1 for the blocks that have pairs or large-h entries, read by K3 (which then enumerates tiles only once):
+    uint32_t *pcount;                   // pairs of particle i
+    uint32_t *pmask;                    // bit m: image m is tiled, bit 16 + m: image m is on the large-h list
 };
 
 
@@ -131,7 +134,7 @@ __device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double 
 // per-particle body of K1: classification, pair / large-h counts, direct deposit, record
 template <int SHAPE, bool DEPOSIT, int NP, bool PER>
 __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0, double pb0, double h, double *coef /* [NP] props */,
-                                             Rec *__restrict__ rec, uint32_t &npairs, uint32_t &nhuge)
+                                             Rec *__restrict__ rec, uint32_t &npairs, uint32_t &nhuge, uint32_t &mask)
 {
     const double R2 = radius2(h);
     const double h2 = AST_DMUL(2.0, h);
@@ -163,9 +166,11 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
             if (DEPOSIT) deposit_small<SHAPE, NP>(p, b.bb, pa, pb, R2, inv_h2, coef);
         } else if (b.cls == CLS_TILED) {
             npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
+            mask |= 1u << m;
             need_rec = true;
         } else if (b.cls == CLS_HUGE) {
             ++nhuge;
+            mask |= 1u << (16 + m);
             need_rec = true;
         }
     }
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict_
     __shared__ uint32_t red[34];
     const int64_t blk = (int64_t)blockIdx.x + block_offset;
     const int64_t i = blk * kBinThreads + threadIdx.x;
-    uint32_t npairs = 0, nhuge = 0;
+    uint32_t npairs = 0, nhuge = 0, mask = 0;
     if (i < p.n) {
         // every load of this particle is issued before anything depends on one of them
         const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i];
@@ -196,10 +201,11 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict_
 #pragma unroll
             for (int k = 0; k < NP; ++k) coef[k] = p.prop[k][i];
         }
-        bin_particle<SHAPE, DEPOSIT, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
+        bin_particle<SHAPE, DEPOSIT, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge, mask);
     }
     // one reduction for both counts: per block pairs <= 256 * 9 * 256 < 2^20 and large-h entries <= 256 * 9 < 2^12
     const uint32_t packed = block_sum_u32((nhuge << 20) | npairs, red);
+    if (packed != 0u && i < p.n) { p.pcount[i] = npairs; p.pmask[i] = mask; }     // K3 only visits blocks with entries
     if (threadIdx.x == 0) {
         block_pairs[blk] = packed & 0xfffffu;
         block_huge[blk] = packed >> 20;
@@ -283,12 +289,16 @@ __global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restr
         double coef[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) coef[k] = st[s].prop[k][tid];
-        uint32_t npairs = 0, nhuge = 0;
-        bin_particle<SHAPE, true, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge);
+        uint32_t npairs = 0, nhuge = 0, mask = 0;
+        bin_particle<SHAPE, true, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge, mask);
         // one barrier-with-vote tells whether any thread has pairs / large-h entries at all (in the direct-deposit regime none
         // has): only then pay for the full block reduction.  The barrier also releases stage s for the next bulk copy.
         uint32_t packed = (nhuge << 20) | npairs;
-        if (__syncthreads_or(packed != 0u)) packed = block_sum_u32(packed, red);
+        if (__syncthreads_or(packed != 0u)) {
+            p.pcount[i] = npairs;
+            p.pmask[i] = mask;
+            packed = block_sum_u32(packed, red);
+        }
         if (tid == 0) {
             block_pairs[blk] = packed & 0xfffffu;
             block_huge[blk] = packed >> 20;
@@ -309,26 +319,21 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
     const bool any_huge = write_huge && hnext > hbase;
     if (!any_pairs && !any_huge) return;                    // uniform for the block
     const int64_t i = (int64_t)blockIdx.x * kBinThreads + threadIdx.x;
-    double pa0 = 0, pb0 = 0, h = 0, R2 = 0;
-    uint32_t npairs = 0, nhuge = 0;
+    // counts and image masks come from K1 (it wrote them for every block that has entries): one enumeration here, not two
+    uint32_t npairs = 0, nhuge = 0, mask = 0;
     if (i < p.n) {
-        pa0 = p.pos[3 * i + p.a_col]; pb0 = p.pos[3 * i + p.b_col]; h = p.h[i];
-        R2 = radius2(h);
-        for (int m = 0; m < p.n_img; ++m) {
-            const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
-            if (!may_touch(p.ax, pa, AST_DMUL(2.0, h)) || !may_touch(p.ay, pb, AST_DMUL(2.0, h))) continue;   // image cannot reach the map
-            Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
-            if (b.cls == CLS_TILED) npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
-            else if (b.cls == CLS_HUGE) ++nhuge;
-        }
+        npairs = p.pcount[i];
+        mask = p.pmask[i];
+        nhuge = (uint32_t)__popc(mask >> 16);
     }
     uint32_t tot;
     uint64_t g = pbase + block_excl_scan_u32(npairs, sm, &tot);
     uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
     if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
+    const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i], R2 = radius2(h);
     for (int m = 0; m < p.n_img; ++m) {
+        if (!((mask >> m) & 0x10001u)) continue;                           // image m has neither pairs nor a large-h entry
         const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
-        if (!may_touch(p.ax, pa, AST_DMUL(2.0, h)) || !may_touch(p.ay, pb, AST_DMUL(2.0, h))) continue;   // image cannot reach the map
         Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
         if (b.cls == CLS_TILED) {
             for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [&](uint32_t key) {
@@ -796,7 +801,7 @@ struct Layout2 {
     uint64_t *scan_tmp;
     Rec *rec;
     uint64_t *pairs_a, *pairs_b, *huge;
-    uint32_t *tbeg, *tend, *seg_off, *seg_tmp;
+    uint32_t *tbeg, *tend, *seg_off, *seg_tmp, *pcount, *pmask;
     void *sort_ws;
     size_t bytes;
 };
@@ -833,6 +838,8 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.block_huge = c.take<uint64_t>(L.nb + 1);
     L.scan_tmp = c.take<uint64_t>(2 * scan_num_blocks(L.nb + 1) + 2);
     L.rec = c.take<Rec>(p->n > 0 ? p->n : 1);
+    L.pcount = c.take<uint32_t>(p->n > 0 ? p->n : 1);
+    L.pmask = c.take<uint32_t>(p->n > 0 ? p->n : 1);
     L.pairs_a = c.take<uint64_t>(L.pair_cap);
     L.pairs_b = c.take<uint64_t>(L.pair_cap);
     L.huge = c.take<uint64_t>(L.huge_cap);
@@ -932,6 +939,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     ast_project2d_stats st;
     memset(&st, 0, sizeof st);
     P2 a = make_p2(p, pos, h, prop, out);
+    a.pcount = L.pcount; a.pmask = L.pmask;
 
     tm.begin(7);
     StageTimer tk((p->flags & AST_FLAG_TIMING) != 0, s);
@@ -1100,6 +1108,7 @@ extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const
     }
     cudaStream_t s = (cudaStream_t)stream;
     P2 a = make_p2(p, pos, h, nullptr, nullptr);
+    a.pcount = L.pcount; a.pmask = L.pmask;
     uint64_t totals[2] = { 0, 0 };
     AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
