@@ -91,20 +91,32 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
         const double x0[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
         const double h = p.h[i], R2 = radius2(h), h2 = 2.0 * h;
         bool need_rec = false;
-        for (int m = 0; m < p.n_img; ++m) {
-            const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
-            if (!may_touch(p.ax[0], q[0], h2) || !may_touch(p.ax[1], q[1], h2) || !may_touch(p.ax[2], q[2], h2)) continue;
-            Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
-            if (b.cls == CLS_SMALL) {
-                if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * norm3(p, h));
-            } else if (b.cls == CLS_TILED) {
-                npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
-                mask |= 1ull << m;
-                need_rec = true;
-            } else if (b.cls == CLS_HUGE) {
-                ++nhuge;
-                mask |= 1ull << (27 + m);
-                need_rec = true;
+        // images m = 9 ia + 3 ib + ic in ascending order; an axis shift that cannot reach the grid prunes its 9 or 3 images at once
+        const int nt = p.n_img == 1 ? 1 : 3;
+        for (int ia = 0; ia < nt; ++ia) {
+            double q[3];
+            q[0] = AST_DADD(x0[0], p.n_img == 1 ? 0.0 : (double)(ia - 1) * p.box[0]);
+            if (!may_touch(p.ax[0], q[0], h2)) continue;
+            for (int ib = 0; ib < nt; ++ib) {
+                q[1] = AST_DADD(x0[1], p.n_img == 1 ? 0.0 : (double)(ib - 1) * p.box[1]);
+                if (!may_touch(p.ax[1], q[1], h2)) continue;
+                for (int ic = 0; ic < nt; ++ic) {
+                    q[2] = AST_DADD(x0[2], p.n_img == 1 ? 0.0 : (double)(ic - 1) * p.box[2]);
+                    if (!may_touch(p.ax[2], q[2], h2)) continue;
+                    const int m = 9 * ia + 3 * ib + ic;
+                    Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
+                    if (b.cls == CLS_SMALL) {
+                        if (DEPOSIT) deposit_small3<SHAPE>(p, b, q, h, R2, p.prop[i] * norm3(p, h));
+                    } else if (b.cls == CLS_TILED) {
+                        npairs += (uint32_t)for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [](uint32_t) {});
+                        mask |= 1ull << m;
+                        need_rec = true;
+                    } else if (b.cls == CLS_HUGE) {
+                        ++nhuge;
+                        mask |= 1ull << (27 + m);
+                        need_rec = true;
+                    }
+                }
             }
         }
         if (need_rec && DEPOSIT) {

@@ -158,20 +158,27 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
         return;
     }
     bool need_rec = false;
-    for (int m = 0; m < n_img; ++m) {
-        const double pa = AST_DADD(pa0, image_shift_a(n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(n_img, p.box_b, m));
-        if (!may_touch(p.ax, pa, AST_DMUL(2.0, h)) || !may_touch(p.ay, pb, AST_DMUL(2.0, h))) continue;   // image cannot reach the map
-        Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
-        if (b.cls == CLS_SMALL) {
-            if (DEPOSIT) deposit_small<SHAPE, NP>(p, b.bb, pa, pb, R2, inv_h2, coef);
-        } else if (b.cls == CLS_TILED) {
-            npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
-            mask |= 1u << m;
-            need_rec = true;
-        } else if (b.cls == CLS_HUGE) {
-            ++nhuge;
-            mask |= 1u << (16 + m);
-            need_rec = true;
+    // images m = 3 ia + ib in ascending order; an x shift that cannot reach the map prunes its three images at once
+    const int nt = n_img == 1 ? 1 : 3;
+    for (int ia = 0; ia < nt; ++ia) {
+        const double pa = AST_DADD(pa0, n_img == 1 ? 0.0 : (double)(ia - 1) * p.box_a);
+        if (!may_touch(p.ax, pa, h2)) continue;                                   // image cannot reach the map
+        for (int ib = 0; ib < nt; ++ib) {
+            const double pb = AST_DADD(pb0, n_img == 1 ? 0.0 : (double)(ib - 1) * p.box_b);
+            if (!may_touch(p.ay, pb, h2)) continue;
+            const int m = 3 * ia + ib;
+            Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+            if (b.cls == CLS_SMALL) {
+                if (DEPOSIT) deposit_small<SHAPE, NP>(p, b.bb, pa, pb, R2, inv_h2, coef);
+            } else if (b.cls == CLS_TILED) {
+                npairs += (uint32_t)for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [](uint32_t) {});
+                mask |= 1u << m;
+                need_rec = true;
+            } else if (b.cls == CLS_HUGE) {
+                ++nhuge;
+                mask |= 1u << (16 + m);
+                need_rec = true;
+            }
         }
     }
     if (need_rec && DEPOSIT) {
