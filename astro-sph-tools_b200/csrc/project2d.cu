@@ -379,6 +379,8 @@ struct Acc {
     double box_a, box_b;
     ShapeTab tab;
     size_t map_stride;
+    const float4 *pp;             // per sorted pair: {fx, fy, sx, sy} tile-relative float32 (pair_record_kernel); null = gather
+    const float2 *pc;             // per sorted pair: weights (x 2 for the cubic spline, whose loops return f/2)
     const uint32_t *seg_off;      // [ntiles + 1] exclusive scan of the segments per tile; seg_off[ntiles] = number of work items
     uint32_t seg_target;          // target list entries per segment
     int ntiles;
@@ -426,6 +428,30 @@ __device__ __forceinline__ bool resolve_work(const Acc &a, TileWork &w)
     w.n_huge = seg == 0 ? a.n_huge : 0u;
     w.atomic_out = nseg > 1;
     return true;
+}
+
+// K5 (default): the same first/last bookkeeping, and every sorted pair is turned into the two things the accumulate kernel
+// needs -- tile-relative float32 coordinates {fx, fy, sx, sy} and the weights -- ONCE, here.  The accumulate kernel used to do
+// this for every pair in each of its 8 warps (sorted pair -> dependent 32-byte record gather -> float64 arithmetic): 10 % of
+// its instructions and 19 % of its stall samples (ncu source view, profiles/r01_v4_summary.md).  Same expressions, same values.
+template <int SHAPE, int NP>
+__global__ void __launch_bounds__(256) pair_record_kernel(Acc a, int64_t n, uint32_t *__restrict__ tbeg, uint32_t *__restrict__ tend,
+                                                          float4 *__restrict__ pp, float2 *__restrict__ pc)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t e = a.sorted[i];
+    const uint32_t key = (uint32_t)(e >> 32), t = key >> a.img_shift, m = key & ((1u << a.img_shift) - 1u);
+    if (i == 0 || ((uint32_t)(a.sorted[i - 1] >> 32) >> a.img_shift) != t) tbeg[t] = (uint32_t)i;
+    if (i == n - 1 || ((uint32_t)(a.sorted[i + 1] >> 32) >> a.img_shift) != t) tend[t] = (uint32_t)(i + 1);
+    const Rec r = a.rec[(uint32_t)e];
+    const int tx = (int)t / a.nty, ty = (int)t - tx * a.nty;
+    const double ox = (double)(tx * TILE), oy = (double)(ty * TILE);
+    const float fx = (float)((r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox);
+    const float fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
+    const float cscale = SHAPE == SHAPE_CUBIC ? 2.0f : 1.0f;
+    pp[i] = make_float4(fx, fy, (float)a.dx * r.inv_h, (float)a.dy * r.inv_h);
+    pc[i] = make_float2(cscale * r.c[0], NP > 1 ? cscale * r.c[1] : 0.f);
 }
 
 // K6: the CTA maps to one 32x32 tile, but every warp walks the tile's list on its own for
@@ -628,27 +654,34 @@ __global__ void __launch_bounds__(256, 4) rowcol_accum_kernel(Acc a)
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 C = make_float2(0.f, 0.f);
         if (j < total) {
-            uint32_t idx, m;
-            if (j < cnt) {
-                const uint64_t e = a.sorted[beg + j];
-                idx = (uint32_t)e;
-                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
+            float fx, fy, sx, sy;
+            if (j < cnt && a.pp != nullptr) {
+                const float4 q = a.pp[beg + j];                  // staged once per pair by pair_record_kernel (coalesced)
+                C = a.pc[beg + j];
+                fx = q.x; fy = q.y; sx = q.z; sy = q.w;
             } else {
-                const uint64_t e = a.huge[j - cnt];
-                idx = (uint32_t)e;
-                m = (uint32_t)(e >> 32);
+                uint32_t idx, m;
+                if (j < cnt) {
+                    const uint64_t e = a.sorted[beg + j];
+                    idx = (uint32_t)e;
+                    m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
+                } else {
+                    const uint64_t e = a.huge[j - cnt];
+                    idx = (uint32_t)e;
+                    m = (uint32_t)(e >> 32);
+                }
+                const Rec r = a.rec[idx];
+                fx = (float)((r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox);
+                fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
+                sx = dxf * r.inv_h; sy = dyf * r.inv_h;
+                C = make_float2(cscale * r.c[0], NP > 1 ? cscale * r.c[1] : 0.f);
             }
-            const Rec r = a.rec[idx];
-            const float fx = (float)((r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox);
-            const float fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
-            const float sx = dxf * r.inv_h, sy = dyf * r.inv_h;
             const float ddx = fmaxf(fmaxf(lox - fx, fx - hix), 0.f) * sx;
             const float ddy = fmaxf(fmaxf(loy - fy, fy - hiy), 0.f) * sy;
             const float qmin2 = ddx * ddx + ddy * ddy;
             hit = qmin2 < 4.0001f;
             outer = hit && SHAPE == SHAPE_CUBIC && qmin2 >= 1.0f;
             P = make_float4(fx * sx, fy * sy, sx, sy);
-            C = make_float2(cscale * r.c[0], NP > 1 ? cscale * r.c[1] : 0.f);
         }
         const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
         const unsigned ball_o = __ballot_sync(0xffffffffu, outer);
@@ -809,6 +842,7 @@ struct Layout2 {
     Rec *rec;
     uint64_t *pairs_a, *pairs_b, *huge;
     uint32_t *tbeg, *tend, *seg_off, *seg_tmp, *pcount, *pmask;
+    float4 *pp;                 // pair_cap staged pair records (the weights reuse the free sort ping-pong buffer)
     void *sort_ws;
     size_t bytes;
 };
@@ -850,6 +884,7 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.pairs_a = c.take<uint64_t>(L.pair_cap);
     L.pairs_b = c.take<uint64_t>(L.pair_cap);
     L.huge = c.take<uint64_t>(L.huge_cap);
+    L.pp = c.take<float4>(L.pair_cap);
     L.tbeg = c.take<uint32_t>(L.ntiles);
     L.tend = c.take<uint32_t>(L.ntiles);
     L.seg_off = c.take<uint32_t>(L.ntiles + 1);
@@ -1056,8 +1091,25 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             AST_CUDA_TRY(cudaMemsetAsync(L.tbeg, 0, sizeof(uint32_t) * L.ntiles, s));
             AST_CUDA_TRY(cudaMemsetAsync(L.tend, 0, sizeof(uint32_t) * L.ntiles, s));
             c.sorted = in_b ? L.pairs_b : L.pairs_a;
+            c.pp = nullptr; c.pc = nullptr;
             if (nw > 0) {
-                tile_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
+                // staged pair records for the default accumulate kernel (AST_PAIR_RECORDS=0: gather inside the kernel instead);
+                // the weights go to the sort's free ping-pong buffer (8 bytes per pair, like the pairs)
+                static int use_records = -1;
+                if (use_records < 0) { const char *e = getenv("AST_PAIR_RECORDS"); use_records = (e && e[0] == '0') ? 0 : 1; }
+                const unsigned nbk = (unsigned)((nw + 255) / 256);
+                if (use_records && accum_variant() == 3) {
+                    float2 *pc = reinterpret_cast<float2 *>(in_b ? L.pairs_a : L.pairs_b);
+#define AST_LAUNCH_PR(SH) do { if (p->n_prop == 1) pair_record_kernel<SH, 1><<<nbk, 256, 0, s>>>(c, nw, L.tbeg, L.tend, L.pp, pc); \
+                               else pair_record_kernel<SH, 2><<<nbk, 256, 0, s>>>(c, nw, L.tbeg, L.tend, L.pp, pc); } while (0)
+                    if (a.shape == SHAPE_CUBIC) AST_LAUNCH_PR(SHAPE_CUBIC);
+                    else if (a.shape == SHAPE_WENDLAND) AST_LAUNCH_PR(SHAPE_WENDLAND);
+                    else AST_LAUNCH_PR(SHAPE_TABLE);
+#undef AST_LAUNCH_PR
+                    c.pp = L.pp; c.pc = pc;
+                } else {
+                    tile_range_kernel<<<nbk, 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
+                }
                 st.n_launches += 1;
             }
             c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
