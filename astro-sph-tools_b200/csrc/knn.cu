@@ -34,8 +34,6 @@ struct KnnArgs {
     const uint32_t *qlist;       // nullable: sorted positions of the queries
     const double *qpos;          // EXTERNAL queries: (nq,3) row-major positions, output row = query index
     int64_t nq, q_begin;
-    const uint32_t *col_off;     // [G*G + 1] exclusive scan of the 32-query chunks per (cx, cy) column (warp-cooperative kernel)
-    int64_t q_end;               // queries = particles with original index in [q_begin, q_end)
     int k;
     double *h_out;
     int32_t *idx_out;
@@ -246,244 +244,152 @@ __global__ void __launch_bounds__(128) knn_query_kernel(KnnArgs a)
 }
 
 
-// ---- warp-cooperative queries ---------------------------------------------------------------------------------------
-// One warp answers 32 consecutive particles of one (cx, cy) column of cells (a run of cells along z, contiguous in the
-// cell-ordered arrays).  All 32 queries walk the SAME candidates: for every ring the warp visits the new columns
-// (cx + ox, cy + oy) over the z-range [zlo - ring, zhi + ring] of the chunk and the two new z-caps of the columns it already
-// knows; each piece is one contiguous particle range (prefix cstart), loaded 32 candidates at a time into shared memory by
-// the whole warp (coalesced) and then read by every lane as a broadcast.  No divergence in the distance loop, candidate
-// loads shared by 32 queries; only the heap insert is per lane.  The thread-per-query kernel above evaluates ~250 candidates
-// per query on 16 of 32 lanes and stalls on scattered gathers; this one evaluates ~860 per query in lock step (23 SASS
-// instructions each) and, as measured, spends as many instructions again in the lock-step heap merges (ncu: 3.5e10 warp
-// instructions, 80 ms at 256^3 against 2.8e10 and 46 ms), so it is NOT the default; it is kept, tested bit-equal to scipy,
-// as the starting point for a selection scheme that does not pay a sift-down per accepted candidate.
-// Arithmetic is scipy's, pair by pair: d2 = (ex*ex + ey*ey) + ez*ez with each delta wrapped by -+box when |delta| > box/2.
-// When every pair of (chunk, candidate piece) provably takes the same wrap branch on an axis (cell offsets at least one cell
-// away from box/2: 2 (|offset| + 2) <= G) the wrap is a per-piece constant shift added to the delta -- the same operation
-// the branch would have performed -- otherwise the per-pair comparison is kept.
-__global__ void knn_col_chunks_kernel(const uint32_t *__restrict__ cstart, int G, uint32_t *__restrict__ col_off)
-{
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col > G * G) return;
-    col_off[col] = col < G * G ? (cstart[(int64_t)col * G + G] - cstart[(int64_t)col * G] + 31u) / 32u : 0u;
-}
+// ---- one thread per query, warp in lock step (default) ---------------------------------------------------------------
+// Same traversal as knn_query_kernel (ring by ring around the query's own cell, whole z-runs of the new columns, two caps of
+// the known ones) but the 32 queries of a warp -- neighbours in cell order -- walk it TOGETHER: every piece of the traversal
+// is executed by all lanes for max-over-lanes iterations (a lane whose own range is shorter or empty idles), accepted
+// candidates are appended to a per-lane pending list with a predicated store, and the lists are merged into the per-lane
+// heaps by all lanes at the same points (when one list could overflow, and before each termination test).  In the diverging
+// kernel 64 % of the stall samples sat in heap inserts executed by 11 of 32 lanes, each accept at its own moment (ncu source
+// view, profiles/r01_v4_secondary_ncu.txt).  The periodic wrap of a piece is a constant shift whenever that is provably what
+// every pair of the piece would do, else the per-pair comparison: a piece lies `off` cells from the query's cell along an
+// axis (|off| <= ring); if it was reached without wrapping, every delta is below (ring + 1) cells, if it was reached by wrapping,
+// every delta exceeds box - (ring + 1) cells in magnitude, and both are a full cell away from box/2 when 2 (ring + 2) <= G.
+constexpr int kQPend = 16;        // 32 measured 3 % slower (staler thresholds, more local memory)
 
-// number of chunks with at least one query of the subset [q_begin, q_end) (decides between the two query kernels)
-__global__ void knn_active_chunks_kernel(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ col_off,
-                                         const uint32_t *__restrict__ sidx, int G, int64_t q_begin, int64_t q_end,
-                                         unsigned long long *__restrict__ count)
+template <int KCAP, bool WANT_IDX, bool EXTERNAL, bool PER>
+__global__ void __launch_bounds__(128) knn_lockstep_kernel(KnnArgs a)
 {
-    const int col = blockIdx.x;
-    const uint32_t b = cstart[(int64_t)col * G], e = cstart[(int64_t)col * G + G];
-    unsigned long long mine = 0;
-    for (uint32_t c = b + 32u * threadIdx.x; c < e; c += 32u * blockDim.x) {
-        bool any = false;
-        for (uint32_t j = c; j < e && j < c + 32u; ++j) any = any || ((int64_t)sidx[j] >= q_begin && (int64_t)sidx[j] < q_end);
-        mine += any ? 1ull : 0ull;
-    }
-    if (mine) atomicAdd(count, mine);
-}
-
-// max-heap in SHARED memory, entry i of lane l at [i * 32 + l] (conflict-free); see knn_block_kernel
-template <bool WANT_IDX>
-struct SHeap {
-    double *d;          // already offset by the lane
-    uint32_t *id;
-    int k;
-    __device__ __forceinline__ double &D(int i) const { return d[i * 32]; }
-    __device__ __forceinline__ uint32_t &I(int i) const { return id[i * 32]; }
-    __device__ __forceinline__ bool less(double d2, uint32_t j, double e2, uint32_t l) const
-    {
-        return WANT_IDX ? (d2 < e2 || (d2 == e2 && j < l)) : (d2 < e2);
-    }
-    __device__ __forceinline__ void replace_root(double d2, uint32_t j)      // 4-ary, as Heap::replace_root
-    {
-        int p = 0;
-        for (;;) {
-            const int c = 4 * p + 1;
-            if (c >= k) break;
-            const int c1 = min(c + 1, k - 1), c2 = min(c + 2, k - 1), c3 = min(c + 3, k - 1);
-            const double e0 = D(c), e1 = D(c1), e2 = D(c2), e3 = D(c3);
-            const uint32_t i0 = WANT_IDX ? I(c) : 0u, i1 = WANT_IDX ? I(c1) : 0u, i2 = WANT_IDX ? I(c2) : 0u, i3 = WANT_IDX ? I(c3) : 0u;
-            int ma = c, mb = c2;
-            double da = e0, db = e2;
-            uint32_t ia = i0, ib = i2;
-            if (less(e0, i0, e1, i1)) { ma = c1; da = e1; ia = i1; }
-            if (less(e2, i2, e3, i3)) { mb = c3; db = e3; ib = i3; }
-            if (less(da, ia, db, ib)) { ma = mb; da = db; ia = ib; }
-            if (!less(d2, j, da, ia)) break;
-            D(p) = da;
-            if (WANT_IDX) I(p) = ia;
-            p = ma;
-        }
-        D(p) = d2;
-        if (WANT_IDX) I(p) = j;
-    }
-};
-
-constexpr int kPend = 16;          // pending-list slots per lane (flush when a lane holds more than kPend - 8)
-__host__ __device__ inline size_t knn_block_warp_bytes(int k, bool want_idx)
-{
-    return (size_t)(k + kPend + 3) * 32 * sizeof(double) + (want_idx ? (size_t)(k + kPend + 1) * 32 * sizeof(uint32_t) : 0);
-}
-
-template <int WARPS, bool WANT_IDX, bool PER>
-__global__ void __launch_bounds__(WARPS * 32) knn_block_kernel(KnnArgs a)
-{
-    // per warp: heap [k][32] doubles, pending [kPend][32], candidates x, y, z [32]; then (lists) the matching uint32 indices
-    extern __shared__ __align__(16) unsigned char knn_smem[];
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *const wd = reinterpret_cast<double *>(knn_smem + (size_t)wib * knn_block_warp_bytes(a.k, WANT_IDX));
-    double *const pend = wd + (size_t)a.k * 32 + lane;                    // pend[t * 32]
-    double *const sx = wd + (size_t)(a.k + kPend) * 32, *const sy = sx + 32, *const sz = sy + 32;
-    uint32_t *const wi = reinterpret_cast<uint32_t *>(sz + 32);
-    uint32_t *const pend_id = wi + (size_t)a.k * 32 + lane;
-    uint32_t *const si = wi + (size_t)(a.k + kPend) * 32;
-    const uint32_t w = blockIdx.x * (uint32_t)WARPS + (uint32_t)wib;      // chunk index
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < a.nq;                                 // invalid lanes shadow query 0 and never accept anything
+    const int64_t tq = valid ? t : 0;
+    const int64_t s = EXTERNAL ? 0 : (a.qlist ? (int64_t)a.qlist[tq] : tq);
+    const double x = EXTERNAL ? a.qpos[3 * tq] : a.xs[s], y = EXTERNAL ? a.qpos[3 * tq + 1] : a.ys[s],
+                 z = EXTERNAL ? a.qpos[3 * tq + 2] : a.zs[s];
     const KnnGrid &g = a.g;
-    const int G = g.G, ncol = G * G;
-    if (w >= a.col_off[ncol]) return;
-    int lo = 0, hi = ncol - 1;                                            // first column with col_off[col + 1] > w
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a.col_off[mid + 1] > w) hi = mid; else lo = mid + 1;
-    }
-    const int col = lo, cx = col / G, cy = col - cx * G;
-    const uint32_t cend = a.cstart[(int64_t)col * G + G];
-    const uint32_t s0 = a.cstart[(int64_t)col * G] + 32u * (w - a.col_off[col]);
-    const uint32_t s = s0 + (uint32_t)lane < cend ? s0 + (uint32_t)lane : s0;      // lanes past the end shadow the first query
-    const uint32_t oi = a.sidx[s];
-    const bool active = s0 + (uint32_t)lane < cend && (int64_t)oi >= a.q_begin && (int64_t)oi < a.q_end;
-    if (!__any_sync(FULL, active)) return;
-    const double x = a.xs[s], y = a.ys[s], z = a.zs[s];
-    const int qc[3] = { cx, cy, cell_coord(g, z, 2) };
+    const int G = g.G;
+    const double box = g.box, half_box = g.half_box;
+    const double *__restrict__ xs = a.xs, *__restrict__ ys = a.ys, *__restrict__ zs = a.zs;
+    const uint32_t *__restrict__ cstart = a.cstart;
+    const int qc[3] = { cell_coord(g, x, 0), cell_coord(g, y, 1), cell_coord(g, z, 2) };
     const double xq[3] = { x, y, z };
-    const int zlo = __reduce_min_sync(FULL, active ? qc[2] : G), zhi = __reduce_max_sync(FULL, active ? qc[2] : -1);
-    const int zspan = zhi - zlo;
 
-    SHeap<WANT_IDX> hp;
+    Heap<KCAP, WANT_IDX> hp;
     hp.k = a.k;
-    hp.d = wd + lane;
-    hp.id = wi + lane;
     for (int i = 0; i < a.k; ++i) {
-        hp.D(i) = INFINITY;
-        if (WANT_IDX) hp.I(i) = 0xffffffffu;
+        hp.d[i] = INFINITY;
+        if (WANT_IDX) hp.id[i] = 0xffffffffu;
     }
-    double kth = active ? INFINITY : -INFINITY;                           // inactive lanes never accept a candidate
-
-    // Selection in lock step: a candidate that beats the lane's current K-th distance is only APPENDED to a small per-lane
-    // pending list (predicated store, no branch); the lists are merged into the heaps by all lanes together when one of them
-    // could overflow with the next 32 candidates, and before every termination test.  Inserting straight into the heap would
-    // run the divergent sift-down for almost every candidate (some lane of the 32 nearly always accepts).
+    double kth = valid ? INFINITY : -INFINITY;
+    double pend[kQPend];
+    uint32_t pend_id[WANT_IDX ? kQPend : 1];
     int cnt = 0;
-    auto offer = [&](double d2, uint32_t oj) {
-        if (WANT_IDX ? d2 <= kth : d2 < kth) {
-            pend[cnt * 32] = d2;
-            if (WANT_IDX) pend_id[cnt * 32] = oj;
-            ++cnt;
-        }
-    };
+    bool done = !valid;
+
     auto flush = [&]() {
         const int mx = __reduce_max_sync(FULL, cnt);
-        for (int t = 0; t < mx; ++t) {
-            if (t < cnt) {
-                const double d2 = pend[t * 32];
-                const uint32_t oj = WANT_IDX ? pend_id[t * 32] : 0u;
-                if (hp.less(d2, oj, hp.D(0), WANT_IDX ? hp.I(0) : 0u)) hp.replace_root(d2, oj);
+        for (int i = 0; i < mx; ++i) {
+            if (i < cnt) {
+                const double d2 = pend[i];
+                const uint32_t oj = WANT_IDX ? pend_id[i] : 0u;
+                if (hp.less(d2, oj, hp.d[0], WANT_IDX ? hp.id[0] : 0u)) hp.replace_root(d2, oj);
             }
         }
         cnt = 0;
-        kth = active ? hp.D(0) : -INFINITY;
+        kth = valid ? hp.d[0] : -INFINITY;
     };
-    // candidates [jb, je): simple = the wrap of every pair is the constant shift (shx, shy, shz)
+    // candidates [jb, je) of THIS lane (empty for a lane that has nothing to visit here); all lanes iterate together
     auto scan_range = [&](uint32_t jb, uint32_t je, bool simple, double shx, double shy, double shz) {
-        for (uint32_t j0 = jb; j0 < je; j0 += 32u) {
-            const uint32_t j = j0 + (uint32_t)lane;
-            __syncwarp();
-            if (j < je) {
-                sx[lane] = a.xs[j]; sy[lane] = a.ys[j]; sz[lane] = a.zs[j];
-                if (WANT_IDX) si[lane] = a.sidx[j];
-            }
-            __syncwarp();
-            const int m = (int)(je - j0 < 32u ? je - j0 : 32u);
-            for (int t0 = 0; t0 < m; t0 += 8) {                            // at most 8 appends per lane between two flush tests
-                const int t1 = min(t0 + 8, m);
-                if (!PER || simple) {
-                    for (int t = t0; t < t1; ++t) {
-                        double ex = sx[t] - x, ey = sy[t] - y, ez = sz[t] - z;
-                        if (PER) { ex = AST_DADD(ex, shx); ey = AST_DADD(ey, shy); ez = AST_DADD(ez, shz); }
-                        offer(AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez)), WANT_IDX ? si[t] : 0u);
+        const int len = (int)(je - jb);
+        const int maxlen = __reduce_max_sync(FULL, len);
+        for (int t0 = 0; t0 < maxlen; t0 += 8) {
+            const int t1 = min(t0 + 8, maxlen);
+            for (int tt = t0; tt < t1; ++tt) {
+                if (tt < len) {
+                    const uint32_t j = jb + (uint32_t)tt;
+                    double ex = xs[j] - x, ey = ys[j] - y, ez = zs[j] - z;
+                    if (PER) {
+                        if (simple) {
+                            ex = AST_DADD(ex, shx); ey = AST_DADD(ey, shy); ez = AST_DADD(ez, shz);
+                        } else {                                   // scipy's per-pair wrap, branch-free (x + 0.0 is x)
+                            ex = AST_DADD(ex, ex < -half_box ? box : (ex > half_box ? -box : 0.0));
+                            ey = AST_DADD(ey, ey < -half_box ? box : (ey > half_box ? -box : 0.0));
+                            ez = AST_DADD(ez, ez < -half_box ? box : (ez > half_box ? -box : 0.0));
+                        }
                     }
-                } else {
-                    for (int t = t0; t < t1; ++t) {
-                        double ex = sx[t] - x, ey = sy[t] - y, ez = sz[t] - z;
-                        if (ex < -g.half_box) ex += g.box; else if (ex > g.half_box) ex -= g.box;
-                        if (ey < -g.half_box) ey += g.box; else if (ey > g.half_box) ey -= g.box;
-                        if (ez < -g.half_box) ez += g.box; else if (ez > g.half_box) ez -= g.box;
-                        offer(AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez)), WANT_IDX ? si[t] : 0u);
+                    const double d2 = AST_DADD(AST_DADD(AST_DMUL(ex, ex), AST_DMUL(ey, ey)), AST_DMUL(ez, ez));
+                    if (WANT_IDX ? d2 <= kth : d2 < kth) {
+                        pend[cnt] = d2;
+                        if (WANT_IDX) pend_id[cnt] = a.sidx[j];
+                        ++cnt;
                     }
                 }
-                if (__any_sync(FULL, cnt > kPend - 8)) flush();
             }
+            if (__any_sync(FULL, cnt > kQPend - 8)) flush();
         }
     };
-    // raw z-cells [z0, z1] (may stick out of [0, G)) of column (ccx, ccy); at most G cells
-    auto scan_z = [&](int ccx, int ccy, int z0, int z1, bool simple_xy, double shx, double shy, int ring) {
+    // raw z-cells [z0, z1] (may stick out of [0, G)) of column (ccx, ccy); `on` = this lane visits the piece at all.
+    // Always the same number of scan_range calls for every lane (two), so the warp stays converged.
+    auto scan_z = [&](bool on, int ccx, int ccy, int z0, int z1, bool simple, double shx, double shy) {
         const uint32_t base = ((uint32_t)ccx * G + ccy) * G;
-        if (!PER) {
-            z0 = max(z0, 0); z1 = min(z1, G - 1);
-            if (z0 <= z1) scan_range(a.cstart[base + z0], a.cstart[base + z1 + 1], true, 0.0, 0.0, 0.0);
-            return;
+        uint32_t b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+        double sh0 = 0.0, sh1 = 0.0;
+        bool smp = simple;
+        if (on) {
+            if (!PER) {
+                z0 = max(z0, 0); z1 = min(z1, G - 1);
+                if (z0 <= z1) { b0 = cstart[base + z0]; e0 = cstart[base + z1 + 1]; }
+            } else if (z1 - z0 + 1 >= G) {
+                b0 = cstart[base]; e0 = cstart[base + G]; smp = false;          // the run closes on itself: every cell once
+            } else if (z0 < 0) {
+                const int zt = min(z1, -1);
+                b0 = cstart[base + z0 + G]; e0 = cstart[base + zt + G + 1]; sh0 = -box;
+                if (z1 >= 0) { b1 = cstart[base]; e1 = cstart[base + z1 + 1]; }
+            } else if (z1 >= G) {
+                const int zb = max(z0, G);
+                if (z0 < G) { b0 = cstart[base + z0]; e0 = cstart[base + G]; }
+                b1 = cstart[base + zb - G]; e1 = cstart[base + z1 - G + 1]; sh1 = box;
+            } else {
+                b0 = cstart[base + z0]; e0 = cstart[base + z1 + 1];
+            }
         }
-        const bool simple = simple_xy && 2 * (zspan + ring + 2) <= G;
-        if (z1 - z0 + 1 >= G) { scan_range(a.cstart[base], a.cstart[base + G], false, 0.0, 0.0, 0.0); return; }
-        if (z0 < 0) {
-            // cells z0+G .. min(z1,-1)+G lie above the chunk after wrapping: raw delta ~ +box -> the pair subtracts box
-            const int zt = min(z1, -1);
-            scan_range(a.cstart[base + z0 + G], a.cstart[base + zt + G + 1], simple, shx, shy, -g.box);
-            if (z1 >= 0) scan_range(a.cstart[base], a.cstart[base + z1 + 1], simple, shx, shy, 0.0);
-        } else if (z1 >= G) {
-            const int zb = max(z0, G);
-            if (z0 < G) scan_range(a.cstart[base + z0], a.cstart[base + G], simple, shx, shy, 0.0);
-            scan_range(a.cstart[base + zb - G], a.cstart[base + z1 - G + 1], simple, shx, shy, g.box);
-        } else {
-            scan_range(a.cstart[base + z0], a.cstart[base + z1 + 1], simple, shx, shy, 0.0);
-        }
+        // `smp` may differ between lanes only through the closed-run case, which depends on ring and G alone: uniform
+        scan_range(b0, e0, smp, shx, shy, sh0);
+        if (PER) scan_range(b1, e1, smp, shx, shy, sh1);
     };
 
     for (int ring = 0;; ++ring) {
-        const int len_prev = zspan + 1 + 2 * (ring - 1);                  // z-cells of a known column before this ring
+        const bool simple = PER && 2 * (ring + 2) <= G;
         for (int ox = -ring; ox <= ring; ++ox) {
-            int ccx = cx + ox;
+            int ccx = qc[0] + ox;
             double shx = 0.0;
+            bool okx = !done;
             if (PER) {
-                if (2 * abs(ox) > G || (2 * abs(ox) == G && ox < 0)) continue;
-                if (ccx < 0) { ccx += G; shx = -g.box; } else if (ccx >= G) { ccx -= G; shx = g.box; }
-            } else if (ccx < 0 || ccx >= G) continue;
+                if (2 * abs(ox) > G || (2 * abs(ox) == G && ox < 0)) continue;          // uniform: depends on ox and G only
+                if (ccx < 0) { ccx += G; shx = -box; } else if (ccx >= G) { ccx -= G; shx = box; }
+            } else if (ccx < 0 || ccx >= G) { okx = false; ccx = 0; }
             for (int oy = -ring; oy <= ring; ++oy) {
-                int ccy = cy + oy;
+                int ccy = qc[1] + oy;
                 double shy = 0.0;
+                bool on = okx;
                 if (PER) {
                     if (2 * abs(oy) > G || (2 * abs(oy) == G && oy < 0)) continue;
-                    if (ccy < 0) { ccy += G; shy = -g.box; } else if (ccy >= G) { ccy -= G; shy = g.box; }
-                } else if (ccy < 0 || ccy >= G) continue;
-                const bool simple_xy = 2 * (abs(ox) + 2) <= G && 2 * (abs(oy) + 2) <= G;
+                    if (ccy < 0) { ccy += G; shy = -box; } else if (ccy >= G) { ccy -= G; shy = box; }
+                } else if (ccy < 0 || ccy >= G) { on = false; ccy = 0; }
                 if (abs(ox) == ring || abs(oy) == ring) {
-                    scan_z(ccx, ccy, zlo - ring, zhi + ring, simple_xy, shx, shy, ring);          // new column: whole z-range
+                    scan_z(on, ccx, ccy, qc[2] - ring, qc[2] + ring, simple, shx, shy);           // new column: whole z-run
                 } else if (!PER) {
-                    scan_z(ccx, ccy, zlo - ring, zlo - ring, simple_xy, shx, shy, ring);          // known column: the two new caps
-                    scan_z(ccx, ccy, zhi + ring, zhi + ring, simple_xy, shx, shy, ring);
+                    scan_z(on, ccx, ccy, qc[2] - ring, qc[2] - ring, simple, shx, shy);           // known column: two new caps
+                    scan_z(on, ccx, ccy, qc[2] + ring, qc[2] + ring, simple, shx, shy);
                 } else {
-                    // periodic: a cap is new only while the known z-range has not closed on itself
-                    if (len_prev + 1 <= G) scan_z(ccx, ccy, zlo - ring, zlo - ring, simple_xy, shx, shy, ring);
-                    if (len_prev + 2 <= G) scan_z(ccx, ccy, zhi + ring, zhi + ring, simple_xy, shx, shy, ring);
+                    // periodic: a cap is new only while the known z-run (2 ring - 1 cells) has not closed on itself
+                    if (2 * ring <= G) scan_z(on, ccx, ccy, qc[2] - ring, qc[2] - ring, simple, shx, shy);
+                    if (2 * ring + 1 <= G) scan_z(on, ccx, ccy, qc[2] + ring, qc[2] + ring, simple, shx, shy);
                 }
             }
         }
         flush();
-        // per lane: smallest possible distance to anything outside the cube of cells explored around ITS OWN cell (the
-        // warp has explored a superset of it)
         double dmin = INFINITY;
         bool all = true;
 #pragma unroll
@@ -497,25 +403,26 @@ __global__ void __launch_bounds__(WARPS * 32) knn_block_kernel(KnnArgs a)
             all = all && !lo_open && !hi_open;
         }
         const double safe = dmin - 1e-9 * g.cs[0];
-        const bool done = !active || all || (safe > 0.0 && kth < safe * safe);
+        done = done || all || (safe > 0.0 && kth < safe * safe);
+        if (done) kth = -INFINITY;                                // a finished lane accepts nothing more (its heap is final)
         if (__all_sync(FULL, done)) break;
     }
-    if (!active) return;
-    const int64_t row = (int64_t)oi - a.q_begin;
-    if (a.h_out) a.h_out[row] = sqrt(hp.D(0));
+    if (!valid) return;
+    const int64_t row = EXTERNAL ? t : (int64_t)a.sidx[s] - a.q_begin;
+    if (a.h_out) a.h_out[row] = sqrt(hp.d[0]);
     if (WANT_IDX) {
         const int k = a.k;
         for (int end = k - 1; end > 0; --end) {                 // heap-sort in place: ascending (d2, idx)
-            const double dd = hp.D(end);
-            const uint32_t ii = hp.I(end);
-            hp.D(end) = hp.D(0);
-            hp.I(end) = hp.I(0);
+            const double dd = hp.d[end];
+            const uint32_t ii = hp.id[end];
+            hp.d[end] = hp.d[0];
+            hp.id[end] = hp.id[0];
             hp.k = end;
             hp.replace_root(dd, ii);
         }
         for (int i = 0; i < k; ++i) {
-            if (a.idx_out) a.idx_out[row * k + i] = hp.D(i) < INFINITY ? (int32_t)hp.I(i) : -1;
-            if (a.dist_out) a.dist_out[row * k + i] = sqrt(hp.D(i));
+            if (a.idx_out) a.idx_out[row * k + i] = hp.d[i] < INFINITY ? (int32_t)hp.id[i] : -1;
+            if (a.dist_out) a.dist_out[row * k + i] = sqrt(hp.d[i]);
         }
     }
 }
@@ -526,8 +433,6 @@ struct KnnLayout {
     uint64_t *ea, *eb;
     double *xs, *ys, *zs;
     uint32_t *sidx, *cbeg, *qflag, *qlist, *scan_tmp, *cell_tmp;   // cbeg: ncell + 1 counts -> exclusive scan = cstart
-    uint32_t *col_off;                                             // G*G + 1 chunk offsets (warp-cooperative kernel)
-    unsigned long long *active_chunks;
     void *sort_ws;
     size_t bytes;
 };
@@ -563,8 +468,6 @@ static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
     L.sidx = c.take<uint32_t>(n);
     L.cbeg = c.take<uint32_t>(L.ncell + 1);
     L.cell_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(L.ncell + 1));
-    L.col_off = c.take<uint32_t>((int64_t)L.G * L.G + 1);
-    L.active_chunks = c.take<unsigned long long>(1);
     L.qflag = c.take<uint32_t>(n);
     L.qlist = c.take<uint32_t>(n);
     L.scan_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(n));
@@ -582,27 +485,17 @@ static void launch_query(const KnnArgs &a, bool want_idx, cudaStream_t s)
     else knn_query_kernel<KCAP, false, false><<<nb, 128, 0, s>>>(a);
 }
 
-template <int WARPS, bool WANT_IDX, bool PER>
-static cudaError_t launch_block_t(const KnnArgs &a, int64_t n, cudaStream_t s)
+template <int KCAP>
+static void launch_lockstep(const KnnArgs &a, bool want_idx, cudaStream_t s)
 {
-    const size_t smem = WARPS * knn_block_warp_bytes(a.k, WANT_IDX);
-    cudaError_t e = cudaFuncSetAttribute(knn_block_kernel<WARPS, WANT_IDX, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int64_t max_chunks = n / 32 + (int64_t)a.g.G * a.g.G;          // sum over columns of ceil(count / 32) <= this
-    knn_block_kernel<WARPS, WANT_IDX, PER><<<(unsigned)((max_chunks + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(a);
-    return cudaGetLastError();
-}
-template <int WARPS>
-static cudaError_t launch_block_w(const KnnArgs &a, bool want_idx, int64_t n, cudaStream_t s)
-{
+    const unsigned nb = (unsigned)((a.nq + 127) / 128);
     const bool per = a.g.box > 0.0;
-    if (want_idx) return per ? launch_block_t<WARPS, true, true>(a, n, s) : launch_block_t<WARPS, true, false>(a, n, s);
-    return per ? launch_block_t<WARPS, false, true>(a, n, s) : launch_block_t<WARPS, false, false>(a, n, s);
-}
-// warps per block by k: the shared-memory heaps ((k + 19) * 256 bytes per warp, 1.5x with lists) should leave >= 3 blocks per SM
-static cudaError_t launch_block(const KnnArgs &a, bool want_idx, int64_t n, cudaStream_t s)
-{
-    return a.k <= 64 ? launch_block_w<4>(a, want_idx, n, s) : launch_block_w<2>(a, want_idx, n, s);
+#define AST_LS(W, E) do { if (per) knn_lockstep_kernel<KCAP, W, E, true><<<nb, 128, 0, s>>>(a); \
+                         else knn_lockstep_kernel<KCAP, W, E, false><<<nb, 128, 0, s>>>(a); } while (0)
+    if (a.qpos) AST_LS(true, true);
+    else if (want_idx) AST_LS(true, false);
+    else AST_LS(false, false);
+#undef AST_LS
 }
 
 // builds the cell list of `pos` in the workspace (steps 1 and 2) and fills the grid / array part of KnnArgs
@@ -678,35 +571,18 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
     if (rc) return rc;
     a.nq = q_end - q_begin;
     a.q_begin = q_begin;
-    a.q_end = q_end;
     a.h_out = h_out; a.idx_out = idx_out; a.dist_out = dist_out;
     const bool want = idx_out != nullptr || dist_out != nullptr;
-    // warp-cooperative kernel (opt-in, AST_KNN_WARP_COOPERATIVE): 32 consecutive particles of a column of cells per warp.
-    // Measured on B200 (256^3, k = 48): 80 ms against 46 ms for one thread per query -- see the note in DESIGN.md section 7.
-    // With a query subset it only makes sense if the subset is spatially coherent (index ranges of snapshot files are):
-    // count the chunks that hold at least one query and fall back when more than 3x the ideal number would have to run.
-    bool cooperative = (p->flags & AST_KNN_WARP_COOPERATIVE) != 0;
-    if (cooperative) {
-        const int ncol = L.G * L.G;
-        knn_col_chunks_kernel<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, s>>>(L.cbeg, L.G, L.col_off);
-        AST_CUDA_TRY(scan_exclusive<uint32_t>(L.col_off, (int64_t)ncol + 1, L.cell_tmp, nullptr, s));
-        a.col_off = L.col_off;
-        if (subset) {
-            unsigned long long active = 0;
-            AST_CUDA_TRY(cudaMemsetAsync(L.active_chunks, 0, sizeof(unsigned long long), s));
-            knn_active_chunks_kernel<<<(unsigned)ncol, 32, 0, s>>>(L.cbeg, L.col_off, L.sidx, L.G, q_begin, q_end, L.active_chunks);
-            AST_CUDA_TRY(cudaMemcpyAsync(&active, L.active_chunks, sizeof active, cudaMemcpyDeviceToHost, s));
-            AST_CUDA_TRY(cudaStreamSynchronize(s));
-            cooperative = (int64_t)active * 32 <= 3 * a.nq + 3 * 32;
-        }
-    }
-    if (cooperative) {
-        AST_CUDA_TRY(launch_block(a, want, n, s));
-    } else {
+    if (p->flags & AST_KNN_DIVERGING) {
         if (p->k <= 32) launch_query<32>(a, want, s);
         else if (p->k <= 48) launch_query<48>(a, want, s);
         else if (p->k <= 64) launch_query<64>(a, want, s);
         else launch_query<128>(a, want, s);
+    } else {
+        if (p->k <= 32) launch_lockstep<32>(a, want, s);
+        else if (p->k <= 48) launch_lockstep<48>(a, want, s);
+        else if (p->k <= 64) launch_lockstep<64>(a, want, s);
+        else launch_lockstep<128>(a, want, s);
     }
     AST_CUDA_TRY(cudaGetLastError());
     return AST_OK;
@@ -734,13 +610,18 @@ extern "C" int ast_knn_query(const ast_knn_params *p, const double *data_pos, co
     a.qpos = query_pos;
     a.nq = n_query;
     a.q_begin = 0;
-    a.q_end = p->n;
-    a.col_off = nullptr;
     a.h_out = nullptr; a.idx_out = idx_out; a.dist_out = dist_out;
-    if (p->k <= 32) launch_query<32>(a, true, s);
-    else if (p->k <= 48) launch_query<48>(a, true, s);
-    else if (p->k <= 64) launch_query<64>(a, true, s);
-    else launch_query<128>(a, true, s);
+    if (p->flags & AST_KNN_DIVERGING) {
+        if (p->k <= 32) launch_query<32>(a, true, s);
+        else if (p->k <= 48) launch_query<48>(a, true, s);
+        else if (p->k <= 64) launch_query<64>(a, true, s);
+        else launch_query<128>(a, true, s);
+    } else {
+        if (p->k <= 32) launch_lockstep<32>(a, true, s);
+        else if (p->k <= 48) launch_lockstep<48>(a, true, s);
+        else if (p->k <= 64) launch_lockstep<64>(a, true, s);
+        else launch_lockstep<128>(a, true, s);
+    }
     AST_CUDA_TRY(cudaGetLastError());
     return AST_OK;
 }

@@ -165,7 +165,9 @@ int ast_bin3d(const ast_grid3d_params *p, const double *pos, const double *h, in
  *   positions must satisfy 0 <= x < box.  idx_out (nullable): N*k int32 neighbour indices, ascending
  *   (distance, index).  dist_out (nullable): N*k float64.  Positions must lie in [lo, hi] per axis (open
  *   box) -- the cell grid is built over that extent. */
-enum { AST_KNN_WARP_COOPERATIVE = 2 };   /* flags: use the warp-cooperative query kernel (default: one thread per query, faster as measured) */
+/* flags: AST_KNN_DIVERGING selects the first query kernel (every thread walks its traversal on its own) instead of the
+ * default, in which the 32 queries of a warp walk their traversals in lock step (tuning / tests). */
+enum { AST_KNN_DIVERGING = 1 };
 typedef struct ast_knn_params {
     int64_t n;
     int32_t k;

@@ -106,35 +106,36 @@ def test_nearest_halo_lookup_separate_query_set(oracle):
 
 @pytest.mark.parametrize("n,k,box,ct", [(30000, 48, 1.0, 0.0), (30000, 48, None, 0.0), (2000, 8, 1.0, 60.0), (700, 16, 1.0, 90.0),
                                          (900, 4, 1.0, 0.5), (5000, 48, 3.0, 8.0), (64, 8, 1.0, 0.0)])
-def test_both_query_kernels_agree_with_scipy(oracle, n, k, box, ct):
-    """thread-per-query (default) and warp-cooperative kernels; small grids (G = 2..6) take the per-pair wrap path of the
-    cooperative kernel, large ones the constant-shift path"""
+def test_all_query_kernels_agree_with_scipy(oracle, n, k, box, ct):
+    """both query kernels (lock-step thread per query = default, diverging thread per query); small grids (G = 2..6) take
+    the per-pair wrap path, large ones the constant-shift path"""
     rng = np.random.default_rng(n * 7 + k)
     pos = rng.uniform(0, box or 1.0, (n, 3))
     ref = oracle.knn_scipy(pos, k, box, workers=-1)[0]
-    assert np.array_equal(gpu_knn(pos, k, box, cell_target=ct), ref)
-    assert np.array_equal(gpu_knn(pos, k, box, cell_target=ct, warp_cooperative=True), ref)
+    for kernel in ("lockstep", "diverging"):
+        assert np.array_equal(gpu_knn(pos, k, box, cell_target=ct, kernel=kernel), ref), kernel
 
 
-def test_cooperative_kernel_lists_periodic_clustered(oracle):
+def test_neighbour_lists_periodic_clustered_all_kernels(oracle):
     from astro_sph_tools_b200 import synthetic
     pos, _ = synthetic.s2_positions(30000, 1.0, n_haloes=5, seed=11)
-    h, idx, dist = gpu_knn(pos, 24, 1.0, lists=True, warp_cooperative=True)
     h_ref, d_ref, i_ref = oracle.knn_scipy(pos, 24, 1.0, workers=-1)
-    assert np.array_equal(h, h_ref) and np.array_equal(dist, d_ref)
     distinct = np.all(np.diff(d_ref, axis=1) > 0, axis=1)           # rows without exactly tied distances
-    assert distinct.mean() > 0.9 and np.array_equal(idx[distinct], i_ref[distinct])
+    assert distinct.mean() > 0.9
+    for kernel in ("lockstep", "diverging"):
+        h, idx, dist = gpu_knn(pos, 24, 1.0, lists=True, kernel=kernel)
+        assert np.array_equal(h, h_ref) and np.array_equal(dist, d_ref), kernel
+        assert np.array_equal(idx[distinct], i_ref[distinct]), kernel
 
 
 def test_scattered_and_coherent_query_subsets(oracle):
-    """cooperative kernel requested: index ranges of a spatially ordered set run it, index ranges of a shuffled set fall back
-    to one thread per query; both give the slice of the full answer"""
+    """index ranges of a spatially ordered set and of a shuffled set both give the slice of the full answer"""
     from astro_sph_tools_b200 import synthetic
     pos, rng = synthetic.s1_positions(28)                            # lattice order: index ranges are slabs
     full = oracle.knn_scipy(pos, 48, 1.0, workers=-1)[0]
     n = len(pos)
     for lo, hi in ((0, n // 8), (n // 3, n // 2), (n - 100, n)):
-        assert np.array_equal(gpu_knn(pos, 48, 1.0, q_begin=lo, q_count=hi - lo, warp_cooperative=True), full[lo:hi])
+        assert np.array_equal(gpu_knn(pos, 48, 1.0, q_begin=lo, q_count=hi - lo), full[lo:hi])
     perm = rng.permutation(n)
     shuffled = np.ascontiguousarray(pos[perm])
-    assert np.array_equal(gpu_knn(shuffled, 48, 1.0, q_begin=1000, q_count=2500, warp_cooperative=True), full[perm][1000:3500])
+    assert np.array_equal(gpu_knn(shuffled, 48, 1.0, q_begin=1000, q_count=2500), full[perm][1000:3500])
