@@ -386,10 +386,10 @@ struct Acc {
     int ntiles;
 };
 
-// K5b: work items.  A tile whose list is longer than seg_target entries is split into ceil(cnt / seg_target) balanced
-// segments, each accumulated by its own CTA (partial sums then go to the map with float64 atomics instead of a plain
-// read-modify-write).  This keeps every SM busy when few tiles hold most of the pairs: clustered particle sets, the slabs
-// that index-sharded ranks and host batches deposit, and the tail of the last wave.
+// K5b: work items.  A tile whose list is longer than seg_target entries is split into ceil(cnt / seg_target) segments, each
+// accumulated by its own CTA (partial sums then go to the map with float64 atomics instead of a plain read-modify-write).
+// This keeps every SM busy when few tiles hold most of the pairs: clustered particle sets, the slabs that index-sharded
+// ranks and host batches deposit, and the tail of the last wave.
 __device__ __forceinline__ uint32_t tile_segments(uint32_t cnt, uint32_t n_huge, uint32_t seg_target)
 {
     if (cnt + n_huge == 0) return 0u;
@@ -405,10 +405,13 @@ __global__ void tile_segments_kernel(const uint32_t *__restrict__ tbeg, const ui
 
 struct TileWork {
     int tile;
-    uint32_t beg, cnt, n_huge;
+    uint32_t beg, cnt, n_huge;    // the tile's whole list: cnt sorted pairs from beg, then the n_huge large-h entries
+    uint32_t first, step;         // this CTA takes the 32-entry batches starting at first, first + step, ...
     bool atomic_out;
 };
-// work item of this CTA (uniform over the CTA); false: nothing to do
+// work item of this CTA (uniform over the CTA); false: nothing to do.  The segments of a split tile INTERLEAVE its batches
+// (segment s of n takes batches s, s + n, ...): the list is in particle order, i.e. spatially ordered, so a contiguous piece
+// of it would load the 8 warps (sub-tiles) of the CTA very unevenly (measured: +4.5 % on the kernel), a strided sample does not.
 __device__ __forceinline__ bool resolve_work(const Acc &a, TileWork &w)
 {
     const uint32_t b = blockIdx.x;
@@ -419,13 +422,12 @@ __device__ __forceinline__ bool resolve_work(const Acc &a, TileWork &w)
         if (a.seg_off[mid + 1] > b) hi = mid; else lo = mid + 1;
     }
     const uint32_t s0 = a.seg_off[lo], nseg = a.seg_off[lo + 1] - s0, seg = b - s0;
-    const uint32_t tb = a.tbeg[lo], cnt = a.tend[lo] - tb;
-    const uint32_t len = nseg > 1 ? (((cnt + nseg - 1) / nseg + 31u) & ~31u) : cnt;
-    const uint32_t off = seg * len;
     w.tile = lo;
-    w.beg = tb + (off < cnt ? off : cnt);
-    w.cnt = off < cnt ? (cnt - off < len ? cnt - off : len) : 0u;
-    w.n_huge = seg == 0 ? a.n_huge : 0u;
+    w.beg = a.tbeg[lo];
+    w.cnt = a.tend[lo] - w.beg;
+    w.n_huge = a.n_huge;
+    w.first = 32u * seg;
+    w.step = 32u * nseg;
     w.atomic_out = nseg > 1;
     return true;
 }
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
         for (int j = 0; j < NPIX; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
 
     int since_fold = 0;
-    for (uint32_t base = 0; base < total; base += 32) {
+    for (uint32_t base = w.first; base < total; base += w.step) {
         const uint32_t j = base + lane;
         bool hit = false, outer = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(256, 4) rowcol_accum_kernel(Acc a)
         for (int j = 0; j < NPIX; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
 
     int since_fold = 0;
-    for (uint32_t base = 0; base < total; base += 32) {
+    for (uint32_t base = w.first; base < total; base += w.step) {
         const uint32_t j = base + lane;
         bool hit = false, outer = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1117,9 +1119,10 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             {
                 static int sm_count = 0;
                 if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-                // enough items for ~4 waves of the resident CTA slots; AST_SEG_WAVES overrides (tuning knob)
+                // enough items for ~32 waves of the resident CTA slots (measured at config 2: 35.1 ms un-split, 34.4 / 34.0 ms
+                // at 16 / 64 waves -- short items even out the tail); AST_SEG_WAVES overrides (tuning knob)
                 static int waves = 0;
-                if (waves == 0) { const char *e = getenv("AST_SEG_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
+                if (waves == 0) { const char *e = getenv("AST_SEG_WAVES"); waves = e ? atoi(e) : 32; if (waves < 1) waves = 1; }
                 const int64_t want_items = (int64_t)sm_count * 4 * waves;
                 int64_t target = (nw / want_items + 31) & ~(int64_t)31;
                 target = target < 1024 ? 1024 : (target > 65536 ? 65536 : target);
