@@ -13,6 +13,7 @@
 #include "block_utils.cuh"
 #include "common.cuh"
 #include "scan_sort.cuh"
+#include "work_items.cuh"
 
 namespace ast {
 
@@ -200,9 +201,11 @@ struct Acc3 {
     int n[3], nb[3], img_shift, n_img;
     double box[3];
     ShapeTab tab;
+    const uint32_t *seg_off;     // work items over the brick lists (work_items.cuh); ntiles = number of bricks
+    int ntiles;
 };
 
-// One CTA per brick, four autonomous warps (no CTA barrier): warp w owns the 4x4x8 column (x,y quadrant) of the brick and
+// One CTA per work item of a brick (a whole brick list, or an interleaved share of a long one), four autonomous warps (no CTA barrier): warp w owns the 4x4x8 column (x,y quadrant) of the brick and
 // walks the brick's list on its own, 32 entries at a time: every lane stages one entry (float64 -> brick-relative float32),
 // tests it against the warp's column, hits are compacted into the warp's shared-memory slots with a ballot (entries whose
 // column lies wholly in the outer annulus q >= 1 of the cubic spline go to a second, cheaper loop), then every lane
@@ -212,9 +215,11 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
 {
     __shared__ float4 sP[4][32];        // {ux*sx, uy*sy, uz*sz, c}
     __shared__ float4 sS[4][32];        // {sx, sy, sz, -}
-    const int brick = blockIdx.x;
-    const uint32_t beg = a.tbeg[brick], cnt = a.tend[brick] - beg;
-    const uint32_t total = cnt + a.n_huge;
+    TileWork w;
+    if (!resolve_work(a, w)) return;
+    const int brick = w.tile;
+    const uint32_t beg = w.beg, cnt = w.cnt;
+    const uint32_t total = cnt + w.n_huge;
     if (total == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bz = brick % a.nb[2], by = (brick / a.nb[2]) % a.nb[1], bx = brick / (a.nb[2] * a.nb[1]);
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
     double acc64[4] = { 0.0, 0.0, 0.0, 0.0 };
     int since_fold = 0;
 
-    for (uint32_t base = 0; base < total; base += 32) {
+    for (uint32_t base = w.first; base < total; base += w.step) {
         const uint32_t j = base + lane;
         bool hit = false, outer = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f), S = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -311,7 +316,10 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
         double *row = a.out + ((size_t)xi * a.n[1] + yi) * a.n[2];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (Z0 + zl + k < a.n[2]) row[Z0 + zl + k] += acc64[k] + (double)acc[k];
+            if (Z0 + zl + k < a.n[2]) {
+                const double v = acc64[k] + (double)acc[k];
+                if (w.atomic_out) atomicAdd(row + Z0 + zl + k, v); else row[Z0 + zl + k] += v;
+            }
     }
 }
 
@@ -341,7 +349,7 @@ struct Layout3 {
     uint32_t *pcount;
     uint64_t *pmask;
     uint64_t *pairs_a, *pairs_b, *huge;
-    uint32_t *tbeg, *tend;
+    uint32_t *tbeg, *tend, *seg_off, *seg_tmp;
     void *sort_ws;
     size_t bytes;
 };
@@ -384,6 +392,8 @@ static Layout3 layout3(const ast_grid3d_params *p, void *ws)
     L.huge = c.take<uint64_t>(L.huge_cap);
     L.tbeg = c.take<uint32_t>(L.nbricks);
     L.tend = c.take<uint32_t>(L.nbricks);
+    L.seg_off = c.take<uint32_t>(L.nbricks + 1);
+    L.seg_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(L.nbricks + 1));
     L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
     L.bytes = c.bytes();
     return L;
@@ -510,12 +520,22 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
             if (nw > 0) brick_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
             tk.end();
             c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
+            // work items: long brick lists (cluster cores) are shared by several CTAs, see work_items.cuh
+            static int sm_count = 0;
+            if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+            const uint32_t seg_target = segment_target(nw, (int64_t)sm_count * 8);
+            c.seg_off = L.seg_off; c.ntiles = (int)L.nbricks;
+            tile_segments_kernel<<<(unsigned)((L.nbricks + 1 + 255) / 256), 256, 0, s>>>(L.tbeg, L.tend, c.n_huge, seg_target, (int)L.nbricks,
+                                                                                     L.seg_off);
+            int nls = 0;
+            AST_CUDA_TRY(scan_exclusive<uint32_t>(L.seg_off, L.nbricks + 1, L.seg_tmp, nullptr, s, &nls));
+            const int64_t max_items = L.nbricks + nw / (int64_t)seg_target;
             tk.begin(5);
-            if (a.shape == SHAPE_CUBIC) brick_accum_kernel<SHAPE_CUBIC><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
-            else if (a.shape == SHAPE_WENDLAND) brick_accum_kernel<SHAPE_WENDLAND><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
-            else brick_accum_kernel<SHAPE_TABLE><<<(unsigned)L.nbricks, kAcc3Threads, 0, s>>>(c);
+            if (a.shape == SHAPE_CUBIC) brick_accum_kernel<SHAPE_CUBIC><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
+            else if (a.shape == SHAPE_WENDLAND) brick_accum_kernel<SHAPE_WENDLAND><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
+            else brick_accum_kernel<SHAPE_TABLE><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
             tk.end();
-            st.n_launches += 3 + nl;
+            st.n_launches += 4 + nl + nls;
             AST_CUDA_TRY(cudaGetLastError());
         }
         st.n_rounds = rounds;

@@ -26,6 +26,7 @@
 #include "block_utils.cuh"
 #include "common.cuh"
 #include "scan_sort.cuh"
+#include "work_items.cuh"
 
 namespace ast {
 
@@ -385,52 +386,6 @@ struct Acc {
     uint32_t seg_target;          // target list entries per segment
     int ntiles;
 };
-
-// K5b: work items.  A tile whose list is longer than seg_target entries is split into ceil(cnt / seg_target) segments, each
-// accumulated by its own CTA (partial sums then go to the map with float64 atomics instead of a plain read-modify-write).
-// This keeps every SM busy when few tiles hold most of the pairs: clustered particle sets, the slabs that index-sharded
-// ranks and host batches deposit, and the tail of the last wave.
-__device__ __forceinline__ uint32_t tile_segments(uint32_t cnt, uint32_t n_huge, uint32_t seg_target)
-{
-    if (cnt + n_huge == 0) return 0u;
-    return cnt <= seg_target ? 1u : (cnt + seg_target - 1) / seg_target;
-}
-__global__ void tile_segments_kernel(const uint32_t *__restrict__ tbeg, const uint32_t *__restrict__ tend, uint32_t n_huge,
-                                     uint32_t seg_target, int ntiles, uint32_t *__restrict__ seg_off)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > ntiles) return;
-    seg_off[t] = t < ntiles ? tile_segments(tend[t] - tbeg[t], n_huge, seg_target) : 0u;
-}
-
-struct TileWork {
-    int tile;
-    uint32_t beg, cnt, n_huge;    // the tile's whole list: cnt sorted pairs from beg, then the n_huge large-h entries
-    uint32_t first, step;         // this CTA takes the 32-entry batches starting at first, first + step, ...
-    bool atomic_out;
-};
-// work item of this CTA (uniform over the CTA); false: nothing to do.  The segments of a split tile INTERLEAVE its batches
-// (segment s of n takes batches s, s + n, ...): the list is in particle order, i.e. spatially ordered, so a contiguous piece
-// of it would load the 8 warps (sub-tiles) of the CTA very unevenly (measured: +4.5 % on the kernel), a strided sample does not.
-__device__ __forceinline__ bool resolve_work(const Acc &a, TileWork &w)
-{
-    const uint32_t b = blockIdx.x;
-    if (b >= a.seg_off[a.ntiles]) return false;
-    int lo = 0, hi = a.ntiles - 1;                 // first tile t with seg_off[t + 1] > b
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a.seg_off[mid + 1] > b) hi = mid; else lo = mid + 1;
-    }
-    const uint32_t s0 = a.seg_off[lo], nseg = a.seg_off[lo + 1] - s0, seg = b - s0;
-    w.tile = lo;
-    w.beg = a.tbeg[lo];
-    w.cnt = a.tend[lo] - w.beg;
-    w.n_huge = a.n_huge;
-    w.first = 32u * seg;
-    w.step = 32u * nseg;
-    w.atomic_out = nseg > 1;
-    return true;
-}
 
 // K5 (default): the same first/last bookkeeping, and every sorted pair is turned into the two things the accumulate kernel
 // needs -- tile-relative float32 coordinates {fx, fy, sx, sy} and the weights -- ONCE, here.  The accumulate kernel used to do
@@ -1119,14 +1074,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             {
                 static int sm_count = 0;
                 if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-                // enough items for ~32 waves of the resident CTA slots (measured at config 2: 35.1 ms un-split, 34.4 / 34.0 ms
-                // at 16 / 64 waves -- short items even out the tail); AST_SEG_WAVES overrides (tuning knob)
-                static int waves = 0;
-                if (waves == 0) { const char *e = getenv("AST_SEG_WAVES"); waves = e ? atoi(e) : 32; if (waves < 1) waves = 1; }
-                const int64_t want_items = (int64_t)sm_count * 4 * waves;
-                int64_t target = (nw / want_items + 31) & ~(int64_t)31;
-                target = target < 1024 ? 1024 : (target > 65536 ? 65536 : target);
-                c.seg_off = L.seg_off; c.seg_target = (uint32_t)target; c.ntiles = (int)L.ntiles;
+                c.seg_off = L.seg_off; c.seg_target = segment_target(nw, (int64_t)sm_count * 4); c.ntiles = (int)L.ntiles;
                 tile_segments_kernel<<<(unsigned)((L.ntiles + 1 + 255) / 256), 256, 0, s>>>(L.tbeg, L.tend, c.n_huge, c.seg_target,
                                                                                         (int)L.ntiles, L.seg_off);
                 int nl = 0;
