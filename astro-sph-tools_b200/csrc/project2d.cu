@@ -6,17 +6,19 @@
 // round (scatter by particle, gather by screen tile):
 //
 //   K1 bin_tma_kernel    persistent CTAs, inputs staged through shared memory by the TMA engine (cp.async.bulk + mbarrier);
-//      (+ bin_kernel)    one thread per particle: float64 bbox (ast_geom.h), class, pair count; particles whose
-//                        bbox is a few pixels are deposited right here with float64 atomics (the HBM-bound
+//      (+ bin_kernel)    one thread per particle: float64 bbox (ast_geom.h), class, pair count and image mask; particles
+//                        whose bbox is a few pixels are deposited right here with float64 atomics (the HBM-bound
 //                        regime: inputs are read exactly once); the others get a 32-byte record.
 //   scan                 exclusive scan of the per-block pair counts.
-//   K3 emit_kernel       writes (tile key << 32 | particle) pairs in emit order.
+//   K3 emit_kernel       writes (tile key << 32 | particle) pairs in emit order (one enumeration: counts come from K1).
 //   radix sort           stable, by tile key (scan_sort.cuh).
-//   K5 tile_range_kernel first/last pair of every tile.
-//   K6 subtile_accum_kernel  one CTA per 32x32-pixel tile, 8 autonomous warps each owning an 8x16 sub-tile, 2x2 pixels
-//                        per thread in registers; every warp stages 32 list entries at a time through its own
-//                        shared-memory slots in tile-relative float32 (converted from float64 at staging time), culls
-//                        them against its sub-tile and evaluates the hits; float32 partial sums are folded into
+//   K5 pair_record_kernel  first/last pair of every tile, and per sorted pair the tile-relative float32 coordinates and
+//                        weights the accumulate kernel needs (computed once, stored in list order).
+//   K5b tile_segments    work items: long tile lists are shared by several CTAs with interleaved batches (work_items.cuh).
+//   K6 rowcol_accum_kernel  one CTA per work item of a 32x32-pixel tile, 8 autonomous warps each owning an 8x16 sub-tile,
+//                        2x2 pixels per thread in registers; every warp stages 32 list entries at a time through its own
+//                        shared-memory slots, culls them against its sub-tile, stores the hits' squared row / column
+//                        distances and evaluates them (one MUFU.SQRT per pixel); float32 partial sums are folded into
 //                        float64 accumulators; the tile is written once.  Particles covering more than huge_min_tiles
 //                        tiles are not binned: every tile walks the (short) global list of them and culls per warp.
 #include <string.h>
