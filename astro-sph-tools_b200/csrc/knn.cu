@@ -47,13 +47,104 @@ __host__ __device__ __forceinline__ int cell_coord(const KnnGrid &g, double x, i
     return i;
 }
 
-__global__ void knn_key_kernel(const double *__restrict__ pos, int64_t n, KnnGrid g, uint64_t *__restrict__ elems)
+__global__ void knn_key_kernel(const double *__restrict__ pos, int64_t n, KnnGrid g, const uint32_t *__restrict__ kept,
+                               uint64_t *__restrict__ elems)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t i = kept ? (int64_t)kept[t] : t;               // n = number of kept particles when `kept` is given
     const int cx = cell_coord(g, pos[3 * i], 0), cy = cell_coord(g, pos[3 * i + 1], 1), cz = cell_coord(g, pos[3 * i + 2], 2);
     const uint32_t key = ((uint32_t)cx * g.G + cy) * g.G + cz;
-    elems[i] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)i;
+    elems[t] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)i;
+}
+
+// ---- reach-limited build for a query subset (multi-GPU: every rank answers an index range) ---------------------------
+// Only particles within `margin` of the bounding box of the queries can be among their K nearest neighbours as long as the
+// K-th distance stays below `margin`; the cell list is then built from those particles alone (the sort dominates the build,
+// and it is replicated on every rank otherwise).  The caller verifies h <= margin for every query afterwards and widens.
+struct KnnReach {
+    double lo[3], len[3];        // per axis the queries lie in [lo, lo + len] (periodic: modulo box, the interval may wrap)
+    double margin, box;          // box > 0: periodic
+};
+__device__ __forceinline__ bool knn_in_reach(const KnnReach &r, double x, double y, double z)
+{
+    const double q[3] = { x, y, z };
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double t = q[c] - r.lo[c], d;
+        if (r.box > 0.0) {
+            t -= floor(t / r.box) * r.box;                                   // position along the circle, from lo
+            d = t <= r.len[c] ? 0.0 : fmin(t - r.len[c], r.box - t);
+        } else {
+            d = t < 0.0 ? -t : (t > r.len[c] ? t - r.len[c] : 0.0);
+        }
+        ok = ok && d <= r.margin;
+    }
+    return ok;
+}
+// periodic boxes: which of 64 equal bins per axis hold a query (the host takes the complement of the largest empty arc)
+__global__ void knn_binmask_kernel(const double *__restrict__ pos, int64_t q_begin, int64_t q_end, double box, unsigned long long *__restrict__ masks)
+{
+    unsigned long long m[3] = { 0ull, 0ull, 0ull };
+    for (int64_t i = q_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q_end; i += (int64_t)gridDim.x * blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int b = (int)floor(pos[3 * i + c] / box * 64.0);
+            b = b < 0 ? 0 : (b > 63 ? 63 : b);
+            m[c] |= 1ull << b;
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[c] |= __shfl_xor_sync(0xffffffffu, m[c], o);
+        if ((threadIdx.x & 31) == 0 && m[c]) atomicOr(&masks[c], m[c]);
+    }
+}
+// per-block min / max of the query positions: out[block][6]
+__global__ void __launch_bounds__(256) knn_bbox_kernel(const double *__restrict__ pos, int64_t q_begin, int64_t q_end, double *__restrict__ out)
+{
+    __shared__ double sm[6][8];
+    double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int64_t i = q_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q_end; i += (int64_t)gridDim.x * blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const double v = pos[3 * i + c]; lo[c] = fmin(lo[c], v); hi[c] = fmax(hi[c], v); }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { sm[c][warp] = lo[c]; sm[3 + c][warp] = hi[c]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sm[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fmin(v, sm[threadIdx.x][w]) : fmax(v, sm[threadIdx.x][w]);
+        out[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+__global__ void knn_reach_flag_kernel(const double *__restrict__ pos, int64_t n, KnnReach r, uint32_t *__restrict__ flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = knn_in_reach(r, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]) ? 1u : 0u;
+}
+__global__ void knn_reach_compact_kernel(const double *__restrict__ pos, int64_t n, KnnReach r, const uint32_t *__restrict__ excl,
+                                         uint32_t *__restrict__ kept)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && knn_in_reach(r, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2])) kept[excl[i]] = (uint32_t)i;
+}
+// number of queries whose K-th distance exceeds the margin (their neighbourhood may be incomplete)
+__global__ void knn_unsafe_kernel(const double *__restrict__ h, int64_t nq, double margin, unsigned long long *__restrict__ count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < nq && !(h[i] <= margin);
+    const unsigned b = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
 }
 
 __global__ void knn_gather_kernel(const double *__restrict__ pos, const uint64_t *__restrict__ sorted, int64_t n,
@@ -433,6 +524,9 @@ struct KnnLayout {
     uint64_t *ea, *eb;
     double *xs, *ys, *zs;
     uint32_t *sidx, *cbeg, *qflag, *qlist, *scan_tmp, *cell_tmp;   // cbeg: ncell + 1 counts -> exclusive scan = cstart
+    uint32_t *kept;                                                // reach-limited build: original indices of the kept particles
+    double *bbox_part;                                             // 256 x 6 partial min / max of the query positions
+    unsigned long long *counter;                                   // kept total / unsafe-query count
     void *sort_ws;
     size_t bytes;
 };
@@ -471,6 +565,9 @@ static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
     L.qflag = c.take<uint32_t>(n);
     L.qlist = c.take<uint32_t>(n);
     L.scan_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(n));
+    L.kept = c.take<uint32_t>(n);
+    L.bbox_part = c.take<double>(256 * 6);
+    L.counter = c.take<unsigned long long>(4);
     L.sort_ws = c.take<char>(sort_workspace_bytes(n));
     L.bytes = c.bytes();
     return L;
@@ -499,8 +596,9 @@ static void launch_lockstep(const KnnArgs &a, bool want_idx, cudaStream_t s)
 }
 
 // builds the cell list of `pos` in the workspace (steps 1 and 2) and fills the grid / array part of KnnArgs
+// (kept != nullptr: from the n_build particles listed there only)
 static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout &L, bool subset, int64_t q_begin, int64_t q_end,
-                     cudaStream_t s, KnnArgs &a)
+                     cudaStream_t s, KnnArgs &a, int64_t n_build = -1, const uint32_t *kept = nullptr)
 {
     KnnGrid g;
     g.G = L.G;
@@ -514,9 +612,9 @@ static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout
         g.cs[c] = ext / (double)L.G;
         g.inv_cs[c] = (double)L.G / ext;
     }
-    const int64_t n = p->n;
+    const int64_t n = n_build >= 0 ? n_build : p->n;
     const unsigned nb = (unsigned)((n + 255) / 256);
-    knn_key_kernel<<<nb, 256, 0, s>>>(pos, n, g, L.ea);
+    knn_key_kernel<<<nb, 256, 0, s>>>(pos, n, g, kept, L.ea);
     int in_b = 0;
     AST_CUDA_TRY(radix_sort_u64(L.ea, L.eb, n, 32, ceil_log2_u64((uint64_t)L.ncell), L.sort_ws, s, &in_b));
     const uint64_t *sorted = in_b ? L.eb : L.ea;
@@ -566,25 +664,101 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
     const int64_t n = p->n;
     const bool subset = p->q_count > 0 && p->q_count < n;
     const int64_t q_begin = subset ? p->q_begin : 0, q_end = subset ? p->q_begin + p->q_count : n;
-    KnnArgs a;
-    rc = knn_build(p, pos, L, subset, q_begin, q_end, s, a);
-    if (rc) return rc;
-    a.nq = q_end - q_begin;
-    a.q_begin = q_begin;
-    a.h_out = h_out; a.idx_out = idx_out; a.dist_out = dist_out;
+    const int64_t nq = q_end - q_begin;
     const bool want = idx_out != nullptr || dist_out != nullptr;
-    if (p->flags & AST_KNN_DIVERGING) {
-        if (p->k <= 32) launch_query<32>(a, want, s);
-        else if (p->k <= 48) launch_query<48>(a, want, s);
-        else if (p->k <= 64) launch_query<64>(a, want, s);
-        else launch_query<128>(a, want, s);
-    } else {
-        if (p->k <= 32) launch_lockstep<32>(a, want, s);
-        else if (p->k <= 48) launch_lockstep<48>(a, want, s);
-        else if (p->k <= 64) launch_lockstep<64>(a, want, s);
-        else launch_lockstep<128>(a, want, s);
+    // Reach-limited build (query subsets only, i.e. the per-rank call of a multi-GPU job): build the cell list from the
+    // particles within `margin` of the region the queries occupy, answer, and verify that every K-th distance stayed
+    // below the margin; otherwise double the margin and repeat (it ends with the full build).  AST_KNN_FULL_BUILD skips it.
+    bool limited = subset && !(p->flags & AST_KNN_FULL_BUILD) && nq * 2 <= n;
+    double margin_cells = 4.0;
+    for (;;) {
+        int64_t n_build = -1;
+        double margin = 0.0;
+        if (limited) {
+            KnnReach r;
+            r.box = p->box > 0.0 ? p->box : 0.0;
+            double cs_max = 0.0;
+            for (int c = 0; c < 3; ++c) {
+                double ext = p->box > 0.0 ? p->box : (p->hi[c] - p->lo[c]);
+                if (!(ext > 0.0)) ext = 1.0;
+                cs_max = ext / (double)L.G > cs_max ? ext / (double)L.G : cs_max;
+            }
+            margin = r.margin = margin_cells * cs_max;
+            const unsigned nbq = (unsigned)((nq + 255) / 256 < 256 ? (nq + 255) / 256 : 256);
+            bool whole = true;                                   // the reach covers the whole box on every axis
+            if (r.box > 0.0) {
+                unsigned long long masks[3];
+                AST_CUDA_TRY(cudaMemsetAsync(L.counter, 0, 4 * sizeof(unsigned long long), s));
+                knn_binmask_kernel<<<nbq, 256, 0, s>>>(pos, q_begin, q_end, r.box, L.counter + 1);
+                AST_CUDA_TRY(cudaMemcpyAsync(masks, L.counter + 1, sizeof masks, cudaMemcpyDeviceToHost, s));
+                AST_CUDA_TRY(cudaStreamSynchronize(s));
+                const double w = r.box / 64.0;
+                for (int c = 0; c < 3; ++c) {
+                    // largest circular run of empty bins; the queries lie in its complement
+                    int best_len = 0, best_start = 0;
+                    for (int b0 = 0; b0 < 64; ++b0) {
+                        if ((masks[c] >> b0) & 1ull) continue;
+                        int len = 0;
+                        while (len < 64 && !((masks[c] >> ((b0 + len) & 63)) & 1ull)) ++len;
+                        if (len > best_len) { best_len = len; best_start = b0; }
+                    }
+                    if (best_len == 0) { r.lo[c] = 0.0; r.len[c] = r.box; }
+                    else { r.lo[c] = (double)((best_start + best_len) & 63) * w; r.len[c] = (double)(64 - best_len) * w; }
+                    whole = whole && r.len[c] + 2.0 * r.margin >= r.box;
+                }
+            } else {
+                double part[256 * 6];
+                knn_bbox_kernel<<<nbq, 256, 0, s>>>(pos, q_begin, q_end, L.bbox_part);
+                AST_CUDA_TRY(cudaMemcpyAsync(part, L.bbox_part, sizeof(double) * 6 * nbq, cudaMemcpyDeviceToHost, s));
+                AST_CUDA_TRY(cudaStreamSynchronize(s));
+                for (int c = 0; c < 3; ++c) {
+                    double lo = part[c], hi = part[3 + c];
+                    for (unsigned b = 1; b < nbq; ++b) { lo = part[6 * b + c] < lo ? part[6 * b + c] : lo; hi = part[6 * b + 3 + c] > hi ? part[6 * b + 3 + c] : hi; }
+                    r.lo[c] = lo; r.len[c] = hi - lo;
+                    whole = whole && lo - r.margin <= p->lo[c] && hi + r.margin >= p->hi[c];
+                }
+            }
+            if (whole) {
+                limited = false;
+            } else {
+                const unsigned nbn = (unsigned)((n + 255) / 256);
+                uint32_t total = 0;
+                knn_reach_flag_kernel<<<nbn, 256, 0, s>>>(pos, n, r, L.qflag);
+                AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n, L.scan_tmp, reinterpret_cast<uint32_t *>(L.counter), s));
+                knn_reach_compact_kernel<<<nbn, 256, 0, s>>>(pos, n, r, L.qflag, L.kept);
+                AST_CUDA_TRY(cudaMemcpyAsync(&total, L.counter, sizeof total, cudaMemcpyDeviceToHost, s));
+                AST_CUDA_TRY(cudaStreamSynchronize(s));
+                if ((int64_t)total * 10 > n * 8) limited = false;          // nearly everything is in reach: nothing to gain
+                else n_build = (int64_t)total;
+            }
+        }
+        KnnArgs a;
+        rc = knn_build(p, pos, L, subset, q_begin, q_end, s, a, limited ? n_build : -1, limited ? L.kept : nullptr);
+        if (rc) return rc;
+        a.nq = nq;
+        a.q_begin = q_begin;
+        a.h_out = h_out; a.idx_out = idx_out; a.dist_out = dist_out;
+        if (p->flags & AST_KNN_DIVERGING) {
+            if (p->k <= 32) launch_query<32>(a, want, s);
+            else if (p->k <= 48) launch_query<48>(a, want, s);
+            else if (p->k <= 64) launch_query<64>(a, want, s);
+            else launch_query<128>(a, want, s);
+        } else {
+            if (p->k <= 32) launch_lockstep<32>(a, want, s);
+            else if (p->k <= 48) launch_lockstep<48>(a, want, s);
+            else if (p->k <= 64) launch_lockstep<64>(a, want, s);
+            else launch_lockstep<128>(a, want, s);
+        }
+        AST_CUDA_TRY(cudaGetLastError());
+        if (!limited) break;
+        unsigned long long unsafe = 0;
+        AST_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned long long), s));
+        knn_unsafe_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(h_out, nq, margin, L.counter);
+        AST_CUDA_TRY(cudaMemcpyAsync(&unsafe, L.counter, sizeof unsafe, cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaStreamSynchronize(s));
+        if (unsafe == 0) break;
+        margin_cells *= 2.0;                                     // some neighbourhood may reach beyond the margin: widen
     }
-    AST_CUDA_TRY(cudaGetLastError());
     return AST_OK;
 }
 

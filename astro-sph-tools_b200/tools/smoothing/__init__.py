@@ -29,7 +29,7 @@ class SmoothingLengthSolver:
         self._ws = None
 
     def solve(self, pos, k=DEFAULT_K, box_size=None, q_begin=0, q_count=0, want_neighbours=False, want_distances=False,
-              stream=None, kernel="lockstep"):
+              stream=None, kernel="lockstep", full_build=False):
         """pos: (N,3) float64 CUDA tensor.  Returns h (Q,) [, idx (Q,k) int32] [, dist (Q,k)] as CUDA tensors where
         Q = q_count or N.  Multi-GPU use: every rank passes all positions and its own [q_begin, q_begin+q_count)."""
         torch = self.torch
@@ -37,7 +37,7 @@ class SmoothingLengthSolver:
             raise ValueError("pos must be a contiguous float64 CUDA tensor of shape (N, 3)")
         n = pos.shape[0]
         p = _lib.KnnParams()
-        p.n = n; p.k = int(k); p.flags = {"lockstep": 0, "diverging": 1}[kernel]      # AST_KNN_* query-kernel selection (csrc/knn.cu)
+        p.n = n; p.k = int(k); p.flags = {"lockstep": 0, "diverging": 1}[kernel] | (4 if full_build else 0)      # AST_KNN_* query-kernel selection (csrc/knn.cu)
         p.box = float(box_size) if box_size else 0.0
         if p.box <= 0.0 and n > 0:
             lo = pos.min(dim=0).values.cpu(); hi = pos.max(dim=0).values.cpu()

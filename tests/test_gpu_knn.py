@@ -139,3 +139,32 @@ def test_scattered_and_coherent_query_subsets(oracle):
     perm = rng.permutation(n)
     shuffled = np.ascontiguousarray(pos[perm])
     assert np.array_equal(gpu_knn(shuffled, 48, 1.0, q_begin=1000, q_count=2500), full[perm][1000:3500])
+
+
+@pytest.mark.parametrize("box", [1.0, None])
+def test_reach_limited_build_for_query_subsets(oracle, box):
+    """a query subset (the per-rank call of a multi-GPU job) builds its cell list from the particles within reach only and
+    widens the reach until every K-th distance is covered: same bits as the full build, for slabs, for a slab that wraps
+    around the periodic box, for a scattered subset and for a clustered set with isolated particles"""
+    from astro_sph_tools_b200 import synthetic
+    pos, rng = synthetic.s1_positions(40)                            # lattice order: index ranges are x-slabs
+    if box is None:
+        pos = pos * 3.0 + 5.0
+    n = len(pos)
+    full = oracle.knn_scipy(pos, 48, box, workers=-1)[0]
+    for lo, hi in ((0, n // 8), (3 * n // 8, n // 2), (7 * n // 8, n), (n // 2 - 50, n // 2 + 50)):
+        got = gpu_knn(pos, 48, box, q_begin=lo, q_count=hi - lo)
+        assert np.array_equal(got, full[lo:hi]), (lo, hi)
+        assert np.array_equal(gpu_knn(pos, 48, box, q_begin=lo, q_count=hi - lo, full_build=True), got)
+    shuffled = np.ascontiguousarray(pos[rng.permutation(n)])         # scattered subset: everything is in reach, full build
+    full_s = oracle.knn_scipy(shuffled, 48, box, workers=-1)[0]
+    assert np.array_equal(gpu_knn(shuffled, 48, box, q_begin=100, q_count=n // 10), full_s[100:100 + n // 10])
+    # clustered set sorted along x, plus far-away stragglers whose 48th neighbour lies well beyond the first margin
+    cl, _ = synthetic.s2_positions(30000, 1.0, n_haloes=6, seed=5)
+    cl = cl[np.argsort(cl[:, 0])]
+    if box is None:
+        cl = np.concatenate([cl, np.array([[5.0, 5.0, 5.0], [-3.0, 0.5, 0.5]])])
+    ref = oracle.knn_scipy(cl, 48, box, workers=-1)
+    for lo, hi in ((0, 3000), (12000, 15000), (len(cl) - 2500, len(cl))):
+        h, idx, dist = gpu_knn(cl, 48, box, lists=True, q_begin=lo, q_count=hi - lo)
+        assert np.array_equal(h, ref[0][lo:hi]) and np.array_equal(dist, ref[1][lo:hi]), (lo, hi)
