@@ -56,3 +56,41 @@ def create_images_sharded(positions, smoothing_lengths, particle_properties, ima
         host.copy_(part)
         return host.numpy()
     return None
+
+
+def gather_positions(pos_local, group=None):
+    """All ranks hold consecutive index ranges of the particle set (the reference's per-rank read,
+    io/EAGLE/_SnapshotEAGLE.py:120-130): returns (all positions (N,3) on this rank's device, offset of this rank's range).
+    ONE collective (all-gather; NCCL over NVLink on GPUs), shards may differ in length (padded to the longest)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return pos_local, 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local = torch.tensor([pos_local.shape[0]], dtype=torch.int64, device=pos_local.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(t.item()) for t in sizes]
+    n_max = max(sizes)
+    padded = pos_local
+    if pos_local.shape[0] < n_max:
+        padded = torch.zeros((n_max, 3), dtype=pos_local.dtype, device=pos_local.device)
+        padded[:pos_local.shape[0]] = pos_local
+    parts = [torch.empty((n_max, 3), dtype=pos_local.dtype, device=pos_local.device) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    return torch.cat([p[:m] for p, m in zip(parts, sizes)], dim=0), sum(sizes[:rank])
+
+
+def smoothing_lengths_sharded(pos_local, k=32, box_size=None, group=None, solver=None):
+    """Multi-GPU smoothing lengths: this rank's particles in (a (n_g,3) float64 tensor on its GPU), this rank's h out (n_g,).
+    Positions are all-gathered once (1024^3 x 24 B = 25.8 GB fits every 180 GB GPU); every rank then answers its own index
+    range on a cell list built from the particles within reach of it (ast_knn_h with q_begin / q_count).  `solver` is any
+    object with SmoothingLengthSolver.solve's signature (the CPU tests of this host logic inject a scipy-based one)."""
+    if solver is None:
+        from .tools.smoothing import SmoothingLengthSolver
+        solver = SmoothingLengthSolver()
+    pos_all, offset = gather_positions(pos_local, group)
+    n_local = pos_local.shape[0]
+    if n_local == pos_all.shape[0]:
+        return solver.solve(pos_all, k, box_size)
+    return solver.solve(pos_all, k, box_size, q_begin=offset, q_count=n_local)

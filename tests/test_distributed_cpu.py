@@ -69,3 +69,48 @@ def test_reduce_is_identity_without_process_group():
     from astro_sph_tools_b200.distributed import reduce_maps
     t = torch.arange(6, dtype=torch.float64)
     assert reduce_maps(t) is t
+
+
+class _ScipySolver:
+    """stands in for SmoothingLengthSolver on the CPU (the oracle's scipy call): only the sharding logic is under test"""
+    def solve(self, pos, k, box_size=None, q_begin=0, q_count=0, **kw):
+        import oracle
+        h = oracle.knn_scipy(pos.numpy(), k, box_size)[0]
+        return torch.from_numpy(h[q_begin:q_begin + q_count] if q_count else h)
+
+
+def _knn_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from astro_sph_tools_b200 import distributed as astd
+    pos = np.random.default_rng(5).uniform(0, 1, (2003, 3))
+    lo, hi = (0, 700) if rank == 0 else (700, 2003)                 # unequal shards: the all-gather pads
+    h = astd.smoothing_lengths_sharded(torch.from_numpy(pos[lo:hi].copy()), 16, 1.0, solver=_ScipySolver())
+    ref = oracle.knn_scipy(pos, 16, 1.0)[0]
+    q.put((rank, bool(np.array_equal(h.numpy(), ref[lo:hi]))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_smoothing_lengths_gather_and_slice():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_knn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get() for _ in range(2))
+    assert got == [(0, True), (1, True)]
+
+
+def test_gather_positions_without_process_group():
+    from astro_sph_tools_b200.distributed import gather_positions
+    p = torch.zeros((5, 3), dtype=torch.float64)
+    allp, off = gather_positions(p)
+    assert allp is p and off == 0
