@@ -24,6 +24,20 @@ def _axis_index(projection_axis):
     raise ValueError(f"projection_axis must be a CoordinateAxes member, got {projection_axis!r}")
 
 
+def batch_cuts(n, nb, ramp=True):
+    """Boundaries of the host batches of project_host: nb batches of bn = ceil(n / nb) particles, preceded (ramp) by a
+    quarter and a half batch so that the first, un-hidden host-to-device copy is short and every later copy is shorter
+    than the deposition it hides behind.  Returns (bn, cuts) with cuts[0] = 0 and cuts[-1] = n."""
+    bn = -(-int(n) // max(int(nb), 1))
+    cuts = [0]
+    if ramp and nb >= 2:
+        for frac in (4, 2):
+            cuts.append(min(n, cuts[-1] + max(1, bn // frac)))
+    while cuts[-1] < n:
+        cuts.append(min(n, cuts[-1] + bn))
+    return bn, cuts
+
+
 class Projector2D:
     """Reusable projection context on one CUDA device."""
 
@@ -153,14 +167,7 @@ class Projector2D:
             positions = np.ascontiguousarray(positions)
             smoothing_lengths = np.ascontiguousarray(smoothing_lengths)
             plist = [np.ascontiguousarray(q) for q in plist]
-            bn = -(-n // nb)
-            # batch boundaries: [bn/4, bn/2, bn, bn, ...] when ramping (the copy of batch b+1 stays shorter than the work on b)
-            cuts = [0]
-            if ramp and nb >= 2:
-                for frac in (4, 2):
-                    cuts.append(min(n, cuts[-1] + max(1, bn // frac)))
-            while cuts[-1] < n:
-                cuts.append(min(n, cuts[-1] + bn))
+            bn, cuts = batch_cuts(n, nb, ramp)
             nb = len(cuts) - 1
             with torch.cuda.device(dev):
                 compute = stream if stream is not None else torch.cuda.current_stream()

@@ -115,3 +115,16 @@ def test_strip_units_is_a_view_without_importing_unyt():
     class Q:                      # unyt_quantity-like: only .value
         value = np.ones(3)
     assert np.array_equal(strip_units(Q()), np.ones(3))
+
+
+def test_host_batch_schedule():
+    from astro_sph_tools_b200.tools.projections._engine import batch_cuts
+    for n, nb, ramp in [(7001, 8, True), (7001, 8, False), (16777216, 4, True), (10, 16, True), (5, 2, True), (1, 1, True)]:
+        bn, cuts = batch_cuts(n, nb, ramp)
+        assert cuts[0] == 0 and cuts[-1] == n and all(b > a for a, b in zip(cuts, cuts[1:]))
+        sizes = np.diff(cuts)
+        assert sizes.max() <= bn
+        if ramp and nb >= 2 and n > 4 * nb:
+            assert sizes[0] == bn // 4 and sizes[1] == bn // 2         # short first copies
+            assert all(sizes[i + 1] <= 2 * sizes[i] + 1 for i in range(len(sizes) - 1))   # each copy hides behind the batch before
+    assert batch_cuts(7001, 8, True)[1][:3] == [0, 219, 657] and len(batch_cuts(7001, 8, True)[1]) - 1 == 10
