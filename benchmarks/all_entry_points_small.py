@@ -35,4 +35,4 @@ for kern in ("lockstep", "diverging"):
 t = IonisationTableBase(-np.abs(rng.normal(size=(9, 11, 5))), np.linspace(-8, 2, 9), np.linspace(2, 9, 11), np.linspace(0, 9, 5), redshift_input_index=2)
 v = t.evaluate_at_redshift(rng.uniform([-9, 1], [3, 10], (5000, 2)), 2.2)
 torch.cuda.synchronize()
-print("sanitize_small: ok")
+print("all_entry_points_small: ok")
