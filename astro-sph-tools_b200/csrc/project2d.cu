@@ -575,7 +575,7 @@ struct __align__(16) RowColSlot {
 static_assert(sizeof(RowColSlot) == 160, "slot layout");
 
 template <int SHAPE, int NP>
-__global__ void __launch_bounds__(256, 4) rowcol_accum_kernel(Acc a)
+__global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
 {
     constexpr int NW = 8, WY = 2, SX = 8, SY = 16, PX = 2, PY = 2, LY = SY / PY, NPIX = PX * PY;
     __shared__ RowColSlot sS[NW][32];
