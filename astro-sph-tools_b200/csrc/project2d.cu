@@ -789,7 +789,7 @@ __global__ void kernel_eval_kernel(int kid, const double *__restrict__ r, const 
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-constexpr int64_t kDefaultSmallMaxPx = 16;
+constexpr int64_t kDefaultSmallMaxPx = 36;      // measured (benchmarks/small_max_probe.py): 36 beats 16 by 21 % at 2.2-pixel supports, 64 loses 22 % at 4.5
 constexpr int64_t kDefaultHugeMinTiles = 256;
 
 struct Layout2 {
