@@ -128,3 +128,18 @@ def test_host_batch_schedule():
             assert sizes[0] == bn // 4 and sizes[1] == bn // 2         # short first copies
             assert all(sizes[i + 1] <= 2 * sizes[i] + 1 for i in range(len(sizes) - 1))   # each copy hides behind the batch before
     assert batch_cuts(7001, 8, True)[1][:3] == [0, 219, 657] and len(batch_cuts(7001, 8, True)[1]) - 1 == 10
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/astro_sph_b200.h must compile as C99 (no C++ or CUDA types in it)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "astro_sph_b200.h"\n'
+                   "int main(void) { ast_project2d_params a; ast_grid3d_params g; ast_knn_params k; ast_table_params t;\n"
+                   "  (void)a; (void)g; (void)k; (void)t; return AST_KNN_FULL_BUILD + AST_TABLE_POW10 + AST_FLAG_PERIODIC; }\n")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
