@@ -24,6 +24,25 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *smem /* 
     return t;
 }
 
+__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t *smem /* >= 32 */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    uint64_t t = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0ull;
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) smem[0] = t;
+    }
+    __syncthreads();
+    t = smem[0];
+    __syncthreads();
+    return t;
+}
+
 // exclusive prefix of v over the block (thread order), total in *total
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *smem /* >= 33 */, uint32_t *total)
 {

@@ -29,12 +29,24 @@ void set_error(const char *fmt, ...);          // defined in capi_common.cu (thr
         }                               \
     } while (0)
 
+// environment switches are read once; callers keep the result in a function-local `static const` (thread-safe in C++11)
+inline bool env_flag(const char *name, bool dflt)
+{
+    const char *e = getenv(name);
+    if (!e || !e[0]) return dflt;
+    return e[0] != '0';
+}
+inline int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
 // AST_DEBUG_SYNC=1 in the environment: synchronise after every kernel and name the one that faulted
 inline bool debug_sync_enabled()
 {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("AST_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
+    static const bool v = env_flag("AST_DEBUG_SYNC", false);
+    return v;
 }
 #define AST_KERNEL_CHECK(stream, name)                                                              \
     do {                                                                                            \

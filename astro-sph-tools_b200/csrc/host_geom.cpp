@@ -48,5 +48,18 @@ extern "C" int64_t hostgeom_pairs2d(const double *pos, const double *h, int64_t 
                 ++g;
             });
         }
+    // large-h split: the member tiles of the large-h entries (list order) follow the tiled pairs; the device gives every
+    // entry a warp (huge_tiles_kernel), the membership test and the order are those of for_each_tile2
+    for (int64_t i = 0; i < n; ++i)
+        for (int m = 0; m < n_img; ++m) {
+            double pa = pos[3 * i + ac] + shift_a[m], pb = pos[3 * i + bc] + shift_b[m];
+            double R2 = radius2(h[i]);
+            Bin2 b = classify2<AST_TILE>(ax, ay, pa, pb, h[i], R2, small_max_px, huge_min_tiles);
+            if (b.cls != CLS_HUGE) continue;
+            for_each_tile2<AST_TILE>(ax, ay, pa, pb, R2, b, nty, [&](uint32_t key) {
+                if (g < cap) pairs[g] = ((uint64_t)((key << img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
+                ++g;
+            });
+        }
     return g;
 }

@@ -19,8 +19,11 @@
 //                        2x2 pixels per thread in registers; every warp stages 32 list entries at a time through its own
 //                        shared-memory slots, culls them against its sub-tile, stores the hits' squared row / column
 //                        distances and evaluates them (one MUFU.SQRT per pixel); float32 partial sums are folded into
-//                        float64 accumulators; the tile is written once.  Particles covering more than huge_min_tiles
-//                        tiles are not binned: every tile walks the (short) global list of them and culls per warp.
+//                        float64 accumulators; the tile is written once.
+//   large-h particles    (more than huge_min_tiles tiles: enumerating them inside one thread of K1 / K3 would stall its warp)
+//                        go on a list; huge_tiles_kernel gives every entry a WARP that enumerates its tiles 32 at a time and
+//                        appends (tile, particle) pairs behind the tiled ones, so the same sort / pair records / accumulate
+//                        handle them and no tile ever walks particles that miss it.
 #include <string.h>
 
 #include "ast_geom.h"
@@ -38,10 +41,26 @@ constexpr int kBinThreads = 256;
 struct __align__(32) Rec {
     double pa, pb;             // in-plane position, float64 (tile-relative float32 is derived at staging time)
     float inv_h;               // 1/h, computed in float64 and narrowed once per particle
-    float c[AST_MAX_PROPS];    // prop * norm(h)
-    float pad;
+    float c[AST_MAX_PROPS];    // mantissa of prop * norm(h) in [0.5, 1) (or 0 / inf / NaN), see split_weight
+    int16_t e[AST_MAX_PROPS];  // its binary exponent
 };
 static_assert(sizeof(Rec) == 32, "record is one 32-byte sector");
+
+// The tile kernels work on float32 weights, the reference on float64 in any unit system (a luminosity in erg/s times
+// 1/(pi h^3) with h in Mpc is ~1e48; Msun masses with lengths in cm ~1e-59: both outside float32).  A weight is therefore
+// stored as a float32 mantissa and its own binary exponent; K1 also takes the maximum exponent E_k of every weight field
+// over the call, the staged per-pair weight is mantissa * 2^(e - E_k) <= 1 (weights more than 2^126 below the largest one of
+// the call flush to zero), the tile sums are formed in those units and multiplied by 2^E_k in float64 when they are added to
+// the map.  Powers of two only: no rounding is added anywhere.
+constexpr int kZeroExp = -32768;
+__device__ __forceinline__ void split_weight(double c, float &m, int &e)
+{
+    if (c == 0.0) { m = 0.f; e = kZeroExp; return; }
+    if (!(fabs(c) < INFINITY)) { m = (float)c; e = 0; return; }            // inf / NaN propagate as they do in the reference
+    int ex;
+    m = (float)frexp(c, &ex);
+    e = ex;
+}
 
 struct P2 {
     const double *pos, *h;
@@ -59,6 +78,7 @@ struct P2 {
     // written by K1 for the blocks that have pairs or large-h entries, read by K3 (which then enumerates tiles only once):
     uint32_t *pcount;                   // pairs of particle i
     uint32_t *pmask;                    // bit m: image m is tiled, bit 16 + m: image m is on the large-h list
+    int *wexp;                          // [AST_MAX_PROPS] maximum weight exponent of the call (atomicMax by K1), see split_weight
 };
 
 
@@ -186,9 +206,19 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
     }
     if (need_rec && DEPOSIT) {
         Rec r;
-        r.pa = pa0; r.pb = pb0; r.inv_h = inv_hf; r.pad = 0.f;
+        r.pa = pa0; r.pb = pb0; r.inv_h = inv_hf;
 #pragma unroll
-        for (int k = 0; k < AST_MAX_PROPS; ++k) r.c[k] = k < NP ? (float)coef[k < NP ? k : 0] : 0.f;
+        for (int k = 0; k < AST_MAX_PROPS; ++k) {
+            int e = kZeroExp;
+            r.c[k] = 0.f;
+            if (k < NP) split_weight(coef[k < NP ? k : 0], r.c[k], e);
+            r.e[k] = (int16_t)e;
+            if (k < NP && e != kZeroExp) {                      // one atomic per warp and field: lanes with records agree on a maximum
+                const unsigned peers = __activemask();
+                const int emax = __reduce_max_sync(peers, e);
+                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicMax(p.wexp + k, emax);
+            }
+        }
         rec[i] = r;
     }
 }
@@ -199,7 +229,7 @@ template <int SHAPE, bool DEPOSIT, int NP, bool PER>
 __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
                                                           uint64_t *__restrict__ block_huge, int64_t block_offset)
 {
-    __shared__ uint32_t red[34];
+    __shared__ uint64_t red[34];
     const int64_t blk = (int64_t)blockIdx.x + block_offset;
     const int64_t i = blk * kBinThreads + threadIdx.x;
     uint32_t npairs = 0, nhuge = 0, mask = 0;
@@ -213,12 +243,12 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict_
         }
         bin_particle<SHAPE, DEPOSIT, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge, mask);
     }
-    // one reduction for both counts: per block pairs <= 256 * 9 * 256 < 2^20 and large-h entries <= 256 * 9 < 2^12
-    const uint32_t packed = block_sum_u32((nhuge << 20) | npairs, red);
-    if (packed != 0u && i < p.n) { p.pcount[i] = npairs; p.pmask[i] = mask; }     // K3 only visits blocks with entries
+    // one 64-bit reduction for both counts (pairs of a thread < 2^31 by validate2, large-h entries <= 9)
+    const uint64_t packed = block_sum_u64(((uint64_t)nhuge << 44) | (uint64_t)npairs, red);
+    if (packed != 0ull && i < p.n) { p.pcount[i] = npairs; p.pmask[i] = mask; }     // K3 only visits blocks with entries
     if (threadIdx.x == 0) {
-        block_pairs[blk] = packed & 0xfffffu;
-        block_huge[blk] = packed >> 20;
+        block_pairs[blk] = packed & ((1ull << 44) - 1ull);
+        block_huge[blk] = packed >> 44;
     }
 }
 
@@ -268,7 +298,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restr
 {
     __shared__ BinStage<NP> st[2];
     __shared__ __align__(8) uint64_t bar[2];
-    __shared__ uint32_t red[34];
+    __shared__ uint64_t red[34];
     const int tid = threadIdx.x;
     constexpr uint32_t kBytes = (uint32_t)sizeof(BinStage<NP>);
     if (tid == 0) {
@@ -303,30 +333,31 @@ __global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restr
         bin_particle<SHAPE, true, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge, mask);
         // one barrier-with-vote tells whether any thread has pairs / large-h entries at all (in the direct-deposit regime none
         // has): only then pay for the full block reduction.  The barrier also releases stage s for the next bulk copy.
-        uint32_t packed = (nhuge << 20) | npairs;
-        if (__syncthreads_or(packed != 0u)) {
+        uint64_t packed = ((uint64_t)nhuge << 44) | (uint64_t)npairs;
+        if (__syncthreads_or(packed != 0ull)) {
             p.pcount[i] = npairs;
             p.pmask[i] = mask;
-            packed = block_sum_u32(packed, red);
+            packed = block_sum_u64(packed, red);
         }
         if (tid == 0) {
-            block_pairs[blk] = packed & 0xfffffu;
-            block_huge[blk] = packed >> 20;
+            block_pairs[blk] = packed & ((1ull << 44) - 1ull);
+            block_huge[blk] = packed >> 44;
         }
     }
 }
 
-// K3: pairs with global emit index in [w0, w1) are written to pairs[g - w0]; huge entries when write_huge.
+// K3: pairs with global emit index in [w0, w1) are written to pairs[g - w0]; large-h entries with list index in [h0, h1)
+// to huge[gh - h0] (either window may be empty).
 __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t *__restrict__ pairs_excl,
                                                            const uint64_t *__restrict__ huge_excl, uint64_t w0, uint64_t w1,
                                                            uint64_t *__restrict__ pairs, uint64_t *__restrict__ huge,
-                                                           int write_huge, uint64_t huge_capacity)
+                                                           uint64_t h0, uint64_t h1)
 {
     __shared__ uint32_t sm[34];
     const uint64_t pbase = pairs_excl[blockIdx.x], pnext = pairs_excl[blockIdx.x + 1];
     const uint64_t hbase = huge_excl[blockIdx.x], hnext = huge_excl[blockIdx.x + 1];
     const bool any_pairs = pnext > pbase && pnext > w0 && pbase < w1;
-    const bool any_huge = write_huge && hnext > hbase;
+    const bool any_huge = hnext > hbase && hnext > h0 && hbase < h1;
     if (!any_pairs && !any_huge) return;                    // uniform for the block
     const int64_t i = (int64_t)blockIdx.x * kBinThreads + threadIdx.x;
     // counts and image masks come from K1 (it wrote them for every block that has entries): one enumeration here, not two
@@ -340,22 +371,79 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
     uint64_t g = pbase + block_excl_scan_u32(npairs, sm, &tot);
     uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
     if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
+    if (!any_pairs) mask &= 0xffff0000u;                    // only the large-h entries are wanted
+    if (!any_huge) mask &= 0x0000ffffu;
+    if (mask == 0u) return;
     const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i], R2 = radius2(h);
     for (int m = 0; m < p.n_img; ++m) {
         if (!((mask >> m) & 0x10001u)) continue;                           // image m has neither pairs nor a large-h entry
+        if ((mask >> (16 + m)) & 1u) {                                     // classes come from K1's masks: no re-classification
+            if (gh >= h0 && gh < h1) huge[gh - h0] = ((uint64_t)m << 32) | (uint64_t)(uint32_t)i;
+            ++gh;
+            continue;
+        }
         const double pa = AST_DADD(pa0, image_shift_a(p.n_img, p.box_a, m)), pb = AST_DADD(pb0, image_shift_b(p.n_img, p.box_b, m));
         Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
-        if (b.cls == CLS_TILED) {
-            for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [&](uint32_t key) {
-                if (g >= w0 && g < w1)
-                    pairs[g - w0] = ((uint64_t)((key << p.img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
-                ++g;
-            });
-        } else if (b.cls == CLS_HUGE) {
-            if (write_huge && gh < huge_capacity) huge[gh] = ((uint64_t)m << 32) | (uint64_t)(uint32_t)i;
-            ++gh;
+        for_each_tile2<TILE>(p.ax, p.ay, pa, pb, R2, b, p.nty, [&](uint32_t key) {
+            if (g >= w0 && g < w1)
+                pairs[g - w0] = ((uint64_t)((key << p.img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
+            ++g;
+        });
+    }
+}
+
+// Large-h split: one WARP per entry of the large-h list.  The tile bbox of the entry is enumerated 32 tiles at a time in emit
+// order (tx ascending, then ty ascending) with the same membership test as for_each_tile2 (at least one pixel of tile /\ bbox
+// inside the support).  WRITE = false: hoff[e] = number of member tiles.  WRITE = true: hoff holds the exclusive scan of those
+// counts; pair number g = base + hoff[e] + rank goes to pairs[g - w0] when it falls into the window [w0, w1).  The pairs have
+// the format of the tiled ones, so everything downstream (sort, pair records, accumulate) is shared.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) huge_tiles_kernel(P2 p, const uint64_t *__restrict__ huge, uint32_t n_entries,
+                                                         uint64_t *__restrict__ hoff, uint64_t base, uint64_t w0, uint64_t w1,
+                                                         uint64_t *__restrict__ pairs)
+{
+    const uint32_t e = (uint32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= n_entries) return;                             // uniform for the warp
+    uint64_t g = 0;
+    if (WRITE) {
+        g = base + hoff[e];
+        const uint64_t gend = base + hoff[e + 1];
+        if (gend <= w0 || g >= w1) return;                  // no pair of this entry falls into the window
+    }
+    const uint64_t ent = huge[e];
+    const int64_t i = (int64_t)(uint32_t)ent;
+    const int m = (int)(ent >> 32);
+    const double h = p.h[i], R2 = radius2(h);
+    const double pa = AST_DADD(p.pos[3 * i + p.a_col], image_shift_a(p.n_img, p.box_a, m));
+    const double pb = AST_DADD(p.pos[3 * i + p.b_col], image_shift_b(p.n_img, p.box_b, m));
+    const Bin2 b = classify2<TILE>(p.ax, p.ay, pa, pb, h, R2, p.small_max_px, p.huge_min_tiles);
+    const int nrow = b.ty1 - b.ty0 + 1;
+    const int64_t nt = (int64_t)(b.tx1 - b.tx0 + 1) * (int64_t)nrow;      // <= 0 only if the entry were not CLS_HUGE
+    uint32_t cnt = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t t0 = 0; t0 < nt; t0 += 32) {
+        const int64_t t = t0 + lane;
+        bool in = false;
+        uint32_t key = 0;
+        if (t < nt) {
+            const int tx = b.tx0 + (int)(t / nrow), ty = b.ty0 + (int)(t % nrow);
+            const int xa = tx * TILE > b.bb.x0 ? tx * TILE : b.bb.x0, xb = tx * TILE + TILE - 1 < b.bb.x1 ? tx * TILE + TILE - 1 : b.bb.x1;
+            const int ya = ty * TILE > b.bb.y0 ? ty * TILE : b.bb.y0, yb = ty * TILE + TILE - 1 < b.bb.y1 ? ty * TILE + TILE - 1 : b.bb.y1;
+            in = AST_DADD(min_dist2(p.ax, pa, xa, xb), min_dist2(p.ay, pb, ya, yb)) < R2;
+            key = (uint32_t)(tx * p.nty + ty);
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, in);
+        if (WRITE) {
+            const uint64_t gg = g + (uint64_t)__popc(ball & lt);
+            if (in && gg >= w0 && gg < w1)
+                pairs[gg - w0] = ((uint64_t)((key << p.img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
+            g += (uint64_t)__popc(ball);
+        } else {
+            cnt += (uint32_t)__popc(ball);
         }
     }
+    if (!WRITE && lane == 0) hoff[e] = (uint64_t)cnt;
 }
 
 // K5: first / one-past-last sorted pair of every tile (arrays pre-zeroed)
@@ -373,8 +461,6 @@ __global__ void tile_range_kernel(const uint64_t *__restrict__ sorted, int64_t n
 struct Acc {
     const uint64_t *sorted;
     const uint32_t *tbeg, *tend;
-    const uint64_t *huge;
-    uint32_t n_huge;
     const Rec *rec;
     double *out;
     double x_min, y_min, dx, dy, inv_dx, inv_dy;
@@ -382,11 +468,13 @@ struct Acc {
     double box_a, box_b;
     ShapeTab tab;
     size_t map_stride;
-    const float4 *pp;             // per sorted pair: {fx, fy, sx, sy} tile-relative float32 (pair_record_kernel); null = gather
+    const float4 *pp;             // per sorted pair: {fx, fy, sx, sy} tile-relative float32 (pair_record_kernel)
     const float2 *pc;             // per sorted pair: weights (x 2 for the cubic spline, whose loops return f/2)
     const uint32_t *seg_off;      // [ntiles + 1] exclusive scan of the segments per tile; seg_off[ntiles] = number of work items
     uint32_t seg_target;          // target list entries per segment
+    uint32_t n_huge;              // always 0 here (work_items.cuh is shared with the 3-D grid, which still walks a global list)
     int ntiles;
+    const int *wexp;              // [AST_MAX_PROPS] the float32 weights are relative to 2^wexp[k] (see split_weight)
 };
 
 // K5 (default): the same first/last bookkeeping, and every sorted pair is turned into the two things the accumulate kernel
@@ -410,155 +498,15 @@ __global__ void __launch_bounds__(256) pair_record_kernel(Acc a, int64_t n, uint
     const float fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
     const float cscale = SHAPE == SHAPE_CUBIC ? 2.0f : 1.0f;
     pp[i] = make_float4(fx, fy, (float)a.dx * r.inv_h, (float)a.dy * r.inv_h);
-    pc[i] = make_float2(cscale * r.c[0], NP > 1 ? cscale * r.c[1] : 0.f);
+    // weights relative to 2^E_k (E_k = largest exponent of the call): mantissa * 2^(e - E_k), at most 1 in magnitude
+    const float w0 = ldexpf(r.c[0], max((int)r.e[0] - a.wexp[0], -300));
+    const float w1 = NP > 1 ? ldexpf(r.c[1], max((int)r.e[1] - a.wexp[1], -300)) : 0.f;
+    pc[i] = make_float2(cscale * w0, cscale * w1);
 }
 
-// K6: the CTA maps to one 32x32 tile, but every warp walks the tile's list on its own for
-// its own sub-tile -- no CTA barrier anywhere.  Per 32 list entries: each lane stages one entry (float64 -> tile-relative
-// float32), tests it against the warp's sub-tile, the hits are compacted into the warp's private shared-memory slots with
-// a ballot, then all lanes evaluate the hits for their PX x PY pixel patch.  WX x WY warps tile the 32x32 pixels.
-template <int SHAPE, int NP, int WX, int WY, int PX, int PY>
-__global__ void __launch_bounds__(WX * WY * 32) subtile_accum_kernel(Acc a)
-{
-    constexpr int NW = WX * WY, SX = TILE / WX, SY = TILE / WY, LY = SY / PY, NPIX = PX * PY;
-    static_assert((SX / PX) * LY == 32, "a warp covers its sub-tile exactly");
-    __shared__ float4 sP[NW][32];       // {ux*sx, uy*sy, sx, sy}
-    __shared__ float2 sC[NW][32];       // {c0, c1}
-
-    TileWork w;
-    if (!resolve_work(a, w)) return;
-    const int tile = w.tile;
-    const uint32_t beg = w.beg, cnt = w.cnt;
-    const uint32_t total = cnt + w.n_huge;
-    if (total == 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = tile / a.nty, ty = tile - tx * a.nty;
-    const int X0 = tx * TILE, Y0 = ty * TILE;
-    const int sub_x = SX * (warp / WY), sub_y = SY * (warp % WY);          // sub-tile origin inside the tile
-    const int xl = sub_x + PX * (lane / LY), yl = sub_y + PY * (lane % LY);
-    float xf[PX], yf[PY];
-#pragma unroll
-    for (int i = 0; i < PX; ++i) xf[i] = (float)(xl + i);
-#pragma unroll
-    for (int i = 0; i < PY; ++i) yf[i] = (float)(yl + i);
-    const float lox = (float)sub_x, hix = (float)(sub_x + SX - 1), loy = (float)sub_y, hiy = (float)(sub_y + SY - 1);
-    const float dxf = (float)a.dx, dyf = (float)a.dy;
-    const double ox = (double)X0, oy = (double)Y0;
-
-    float acc[NP][NPIX];
-    double acc64[NP][NPIX];
-#pragma unroll
-    for (int k = 0; k < NP; ++k)
-#pragma unroll
-        for (int j = 0; j < NPIX; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
-
-    int since_fold = 0;
-    for (uint32_t base = w.first; base < total; base += w.step) {
-        const uint32_t j = base + lane;
-        bool hit = false, outer = false;
-        float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 C = make_float2(0.f, 0.f);
-        if (j < total) {
-            uint32_t idx, m;
-            if (j < cnt) {
-                const uint64_t e = a.sorted[beg + j];
-                idx = (uint32_t)e;
-                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
-            } else {
-                const uint64_t e = a.huge[j - cnt];
-                idx = (uint32_t)e;
-                m = (uint32_t)(e >> 32);
-            }
-            const Rec r = a.rec[idx];
-            const float fx = (float)((r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox);
-            const float fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
-            const float sx = dxf * r.inv_h, sy = dyf * r.inv_h;
-            const float ddx = fmaxf(fmaxf(lox - fx, fx - hix), 0.f) * sx;
-            const float ddy = fmaxf(fmaxf(loy - fy, fy - hiy), 0.f) * sy;
-            const float qmin2 = ddx * ddx + ddy * ddy;          // squared distance (in h) from the particle to the sub-tile
-            hit = qmin2 < 4.0001f;
-            outer = hit && SHAPE == SHAPE_CUBIC && qmin2 >= 1.0f;   // every pixel of the sub-tile has q >= 1: f = 2 a^3 only
-            P = make_float4(fx * sx, fy * sy, sx, sy);
-            C = make_float2(r.c[0], NP > 1 ? r.c[1] : 0.f);
-        }
-        // full hits are compacted from the front of the warp's 32 slots, outer-annulus hits from the back
-        const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
-        const unsigned ball_o = __ballot_sync(0xffffffffu, outer);
-        if (hit) {
-            const unsigned lt = (1u << lane) - 1u;
-            const int dst = outer ? 31 - __popc(ball_o & lt) : __popc(ball_f & lt);
-            sP[warp][dst] = P;
-            sC[warp][dst] = C;
-        }
-        __syncwarp();
-        const int nf = __popc(ball_f), no = __popc(ball_o), nh = nf + no;
-        for (int e = 0; e < nf; ++e) {
-            const float4 q = sP[warp][e];
-            const float2 c = sC[warp][e];
-            float ax2[PX], by2[PY];
-#pragma unroll
-            for (int i = 0; i < PX; ++i) { const float t = fmaf(-xf[i], q.z, q.x); ax2[i] = t * t; }
-#pragma unroll
-            for (int i = 0; i < PY; ++i) { const float t = fmaf(-yf[i], q.w, q.y); by2[i] = t * t; }
-#pragma unroll
-            for (int ix = 0; ix < PX; ++ix)
-#pragma unroll
-                for (int iy = 0; iy < PY; ++iy) {
-                    const float f = shape_eval<SHAPE>(fast_sqrt(ax2[ix] + by2[iy]), a.tab);
-                    acc[0][ix * PY + iy] = fmaf(c.x, f, acc[0][ix * PY + iy]);
-                    if (NP > 1) acc[NP - 1][ix * PY + iy] = fmaf(c.y, f, acc[NP - 1][ix * PY + iy]);
-                }
-        }
-        if (SHAPE == SHAPE_CUBIC) {
-            for (int e = 32 - no; e < 32; ++e) {
-                const float4 q = sP[warp][e];
-                float2 c = sC[warp][e];
-                c.x += c.x; c.y += c.y;                          // the factor 2 of f = 2 a^3
-                float ax2[PX], by2[PY];
-#pragma unroll
-                for (int i = 0; i < PX; ++i) { const float t = fmaf(-xf[i], q.z, q.x); ax2[i] = t * t; }
-#pragma unroll
-                for (int i = 0; i < PY; ++i) { const float t = fmaf(-yf[i], q.w, q.y); by2[i] = t * t; }
-#pragma unroll
-                for (int ix = 0; ix < PX; ++ix)
-#pragma unroll
-                    for (int iy = 0; iy < PY; ++iy) {
-                        const float a1 = __saturatef(fmaf(fast_sqrt(ax2[ix] + by2[iy]), -0.5f, 1.0f));
-                        const float f = a1 * a1 * a1;
-                        acc[0][ix * PY + iy] = fmaf(c.x, f, acc[0][ix * PY + iy]);
-                        if (NP > 1) acc[NP - 1][ix * PY + iy] = fmaf(c.y, f, acc[NP - 1][ix * PY + iy]);
-                    }
-            }
-        }
-        __syncwarp();
-        since_fold += nh;
-        if (since_fold >= 96) {          // fold the float32 partial sums into float64 (warp-uniform condition)
-            since_fold = 0;
-#pragma unroll
-            for (int k = 0; k < NP; ++k)
-#pragma unroll
-                for (int jj = 0; jj < NPIX; ++jj) { acc64[k][jj] += (double)acc[k][jj]; acc[k][jj] = 0.f; }
-        }
-    }
-#pragma unroll
-    for (int ix = 0; ix < PX; ++ix) {
-        const int xi = X0 + xl + ix;
-        if (xi >= a.nx) continue;
-#pragma unroll
-        for (int iy = 0; iy < PY; ++iy) {
-            const int yi = Y0 + yl + iy;
-            if (yi >= a.ny) continue;
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
-                const double v = acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
-                if (w.atomic_out) atomicAdd(o, v); else *o += v;
-            }
-        }
-    }
-}
-
-// K6, default variant: same warp-autonomous scheme (8 warps, 8x16 sub-tile per warp, 2x2 pixels per thread), but for
+// K6: one CTA per work item of a 32x32 tile; every warp walks the list on its own for its own 8x16 sub-tile (no CTA
+// barrier anywhere), 2x2 pixels per thread.  Per 32 list entries each lane loads one staged pair record, tests it against the
+// warp's sub-tile, the hits are ballot-compacted into the warp's shared-memory slots, then all lanes evaluate them.  For
 // batches with enough hits the lane that staged an entry also computes the entry's squared x-distances to the 8 pixel
 // columns and squared y-distances to the 16 pixel rows of the sub-tile (in units of h) and stores them with the
 // weights: the evaluating lanes then fetch their two column and two row values (LDS.64 + LDS.128) instead of
@@ -583,8 +531,7 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
     TileWork w;
     if (!resolve_work(a, w)) return;
     const int tile = w.tile;
-    const uint32_t beg = w.beg, cnt = w.cnt;
-    const uint32_t total = cnt + w.n_huge;
+    const uint32_t beg = w.beg, total = w.cnt;
     if (total == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tile / a.nty, ty = tile - tx * a.nty;
@@ -593,11 +540,8 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
     const int xl = sub_x + PX * (lane / LY), yl = sub_y + PY * (lane % LY);
     const float xf[PX] = { (float)xl, (float)(xl + 1) }, yf[PY] = { (float)yl, (float)(yl + 1) };
     const float lox = (float)sub_x, hix = (float)(sub_x + SX - 1), loy = (float)sub_y, hiy = (float)(sub_y + SY - 1);
-    const float dxf = (float)a.dx, dyf = (float)a.dy;
-    const double ox = (double)X0, oy = (double)Y0;
     RowColSlot *const slots = sS[warp];
     // classic view of the same storage: {ux*sx, uy*sy, sx, sy} in ax[0], {c0, c1} in the first half of ax[1]
-    const float cscale = SHAPE == SHAPE_CUBIC ? 2.0f : 1.0f;
 
     float acc[NP][NPIX];
     double acc64[NP][NPIX];
@@ -613,28 +557,9 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 C = make_float2(0.f, 0.f);
         if (j < total) {
-            float fx, fy, sx, sy;
-            if (j < cnt && a.pp != nullptr) {
-                const float4 q = a.pp[beg + j];                  // staged once per pair by pair_record_kernel (coalesced)
-                C = a.pc[beg + j];
-                fx = q.x; fy = q.y; sx = q.z; sy = q.w;
-            } else {
-                uint32_t idx, m;
-                if (j < cnt) {
-                    const uint64_t e = a.sorted[beg + j];
-                    idx = (uint32_t)e;
-                    m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
-                } else {
-                    const uint64_t e = a.huge[j - cnt];
-                    idx = (uint32_t)e;
-                    m = (uint32_t)(e >> 32);
-                }
-                const Rec r = a.rec[idx];
-                fx = (float)((r.pa + image_shift_a(a.n_img, a.box_a, (int)m) - a.x_min) * a.inv_dx - ox);
-                fy = (float)((r.pb + image_shift_b(a.n_img, a.box_b, (int)m) - a.y_min) * a.inv_dy - oy);
-                sx = dxf * r.inv_h; sy = dyf * r.inv_h;
-                C = make_float2(cscale * r.c[0], NP > 1 ? cscale * r.c[1] : 0.f);
-            }
+            const float4 q = a.pp[beg + j];                      // staged once per pair by pair_record_kernel (coalesced)
+            C = a.pc[beg + j];
+            const float fx = q.x, fy = q.y, sx = q.z, sy = q.w;
             const float ddx = fmaxf(fmaxf(lox - fx, fx - hix), 0.f) * sx;
             const float ddy = fmaxf(fmaxf(loy - fy, fy - hiy), 0.f) * sy;
             const float qmin2 = ddx * ddx + ddy * ddy;
@@ -726,6 +651,9 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
                 for (int jj = 0; jj < NPIX; ++jj) { acc64[k][jj] += (double)acc[k][jj]; acc[k][jj] = 0.f; }
         }
     }
+    int wexp[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) wexp[k] = max(a.wexp[k], -4000);
 #pragma unroll
     for (int ix = 0; ix < PX; ++ix) {
         const int xi = X0 + xl + ix;
@@ -737,7 +665,7 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
-                const double v = acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy];
+                const double v = scalbn(acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy], wexp[k]);   // sums are in units of 2^E_k
                 if (w.atomic_out) atomicAdd(o, v); else *o += v;
             }
         }
@@ -792,16 +720,23 @@ __global__ void kernel_eval_kernel(int kid, const double *__restrict__ r, const 
 constexpr int64_t kDefaultSmallMaxPx = 36;      // measured (benchmarks/small_max_probe.py): 36 beats 16 by 21 % at 2.2-pixel supports, 64 loses 22 % at 4.5
 constexpr int64_t kDefaultHugeMinTiles = 256;
 
+// Workspace.  One pair window of pair_capacity elements; more pairs are walked through it in rounds.
+struct RoundSet {
+    float4 *pp;                 // win staged pair records
+    float2 *pc;                 // win staged pair weights (lives in the ping-pong buffer the sort leaves free)
+    uint32_t *tbeg, *tend, *seg_off, *seg_tmp;
+};
 struct Layout2 {
     int64_t nb;                 // bin blocks
     int64_t ntiles;
-    int64_t pair_cap, huge_cap;
+    int64_t win, huge_cap;
     uint64_t *block_pairs, *block_huge;   // nb + 1 each
     uint64_t *scan_tmp;
     Rec *rec;
-    uint64_t *pairs_a, *pairs_b, *huge;
-    uint32_t *tbeg, *tend, *seg_off, *seg_tmp, *pcount, *pmask;
-    float4 *pp;                 // pair_cap staged pair records (the weights reuse the free sort ping-pong buffer)
+    uint64_t *pairs_a, *pairs_b, *huge, *hoff, *hoff_tmp;
+    uint32_t *pcount, *pmask;
+    int *wexp;
+    RoundSet set;
     void *sort_ws;
     size_t bytes;
 };
@@ -821,7 +756,7 @@ static int validate2(const ast_project2d_params *p)
     AST_REQUIRE(p->x_max > p->x_min && p->y_max > p->y_min, "empty or inverted map bounds");
     if (p->flags & AST_FLAG_PERIODIC) AST_REQUIRE(p->box_a > 0 && p->box_b > 0, "periodic projection needs box_a, box_b > 0");
     AST_REQUIRE(p->pair_capacity >= 0 && p->pair_capacity < (1ll << 32), "pair_capacity out of range");
-    AST_REQUIRE(p->huge_capacity >= 0 && p->huge_capacity < (1ll << 32), "huge_capacity out of range");
+    AST_REQUIRE(p->huge_capacity >= 0 && p->huge_capacity < (1ll << 31), "huge_capacity out of range");
     return AST_OK;
 }
 
@@ -831,7 +766,7 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.nb = (p->n + kBinThreads - 1) / kBinThreads;
     if (L.nb < 1) L.nb = 1;
     L.ntiles = (int64_t)((p->nx + TILE - 1) / TILE) * ((p->ny + TILE - 1) / TILE);
-    L.pair_cap = p->pair_capacity > 0 ? p->pair_capacity : 1;
+    L.win = p->pair_capacity > 0 ? p->pair_capacity : 1;
     L.huge_cap = p->huge_capacity > 0 ? p->huge_capacity : 1;
     Carver c(ws);
     L.block_pairs = c.take<uint64_t>(L.nb + 1);
@@ -840,15 +775,19 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.rec = c.take<Rec>(p->n > 0 ? p->n : 1);
     L.pcount = c.take<uint32_t>(p->n > 0 ? p->n : 1);
     L.pmask = c.take<uint32_t>(p->n > 0 ? p->n : 1);
-    L.pairs_a = c.take<uint64_t>(L.pair_cap);
-    L.pairs_b = c.take<uint64_t>(L.pair_cap);
+    L.wexp = c.take<int>(AST_MAX_PROPS);
+    L.pairs_a = c.take<uint64_t>(L.win);
+    L.pairs_b = c.take<uint64_t>(L.win);
     L.huge = c.take<uint64_t>(L.huge_cap);
-    L.pp = c.take<float4>(L.pair_cap);
-    L.tbeg = c.take<uint32_t>(L.ntiles);
-    L.tend = c.take<uint32_t>(L.ntiles);
-    L.seg_off = c.take<uint32_t>(L.ntiles + 1);
-    L.seg_tmp = c.take<uint32_t>(scan_num_blocks(L.ntiles + 1) + 2);
-    L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
+    L.hoff = c.take<uint64_t>(L.huge_cap + 1);
+    L.hoff_tmp = (uint64_t *)c.take<char>(scan_workspace_bytes<uint64_t>(L.huge_cap + 1));
+    L.set.pp = c.take<float4>(L.win);
+    L.set.pc = nullptr;                                   // chosen per round: the sort's free ping-pong buffer
+    L.set.tbeg = c.take<uint32_t>(L.ntiles);
+    L.set.tend = c.take<uint32_t>(L.ntiles);
+    L.set.seg_off = c.take<uint32_t>(L.ntiles + 1);
+    L.set.seg_tmp = c.take<uint32_t>(scan_num_blocks(L.ntiles + 1) + 2);
+    L.sort_ws = c.take<char>(sort_workspace_bytes(L.win));
     L.bytes = c.bytes();
     return L;
 }
@@ -880,33 +819,15 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     a.small_max_px = p->small_max_px >= 0 ? p->small_max_px : kDefaultSmallMaxPx;
     a.huge_min_tiles = p->huge_min_tiles >= 0 ? p->huge_min_tiles : kDefaultHugeMinTiles;
     a.map_stride = (size_t)p->nx * (size_t)p->ny;
+    a.pcount = nullptr; a.pmask = nullptr; a.wexp = nullptr;
     return a;
 }
 
-// AST_ACCUM_VARIANT (tuning knob): 1 = 16x16 sub-tiles (4 warps, 2x4 pixels per thread), 2 = 8x16 sub-tiles (8 warps,
-// 2x2 pixels per thread, coordinates per lane), 3 = default: 8x16 sub-tiles with staged row/column distances
-static int accum_variant()
-{
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("AST_ACCUM_VARIANT"); v = e ? atoi(e) : 3; if (v < 1 || v > 3) v = 3; }
-    return v;
-}
-
-template <int SHAPE, int NP>
-static void launch_accum_np(const Acc &a, int64_t ntiles, cudaStream_t s)
-{
-    switch (accum_variant()) {
-    case 1: subtile_accum_kernel<SHAPE, NP, 2, 2, 2, 4><<<(unsigned)ntiles, 128, 0, s>>>(a); break;
-    case 3: rowcol_accum_kernel<SHAPE, NP><<<(unsigned)ntiles, 256, 0, s>>>(a); break;
-    default: subtile_accum_kernel<SHAPE, NP, 4, 2, 2, 2><<<(unsigned)ntiles, 256, 0, s>>>(a); break;
-    }
-}
-
 template <int SHAPE>
-static void launch_accum(int np, const Acc &a, int64_t ntiles, cudaStream_t s)
+static void launch_accum(int np, const Acc &a, int64_t n_items, cudaStream_t s)
 {
-    if (np == 1) launch_accum_np<SHAPE, 1>(a, ntiles, s);
-    else launch_accum_np<SHAPE, 2>(a, ntiles, s);
+    if (np == 1) rowcol_accum_kernel<SHAPE, 1><<<(unsigned)n_items, 256, 0, s>>>(a);
+    else rowcol_accum_kernel<SHAPE, 2><<<(unsigned)n_items, 256, 0, s>>>(a);
 }
 
 }  // namespace ast
@@ -922,6 +843,89 @@ extern "C" int ast_project2d_workspace_bytes(const ast_project2d_params *p, size
     return AST_OK;
 }
 
+namespace {
+
+// everything one call needs on the host
+struct Run2 {
+    const ast_project2d_params *p;
+    P2 a;
+    Layout2 L;
+    Acc c;
+    cudaStream_t s;
+    float2 *pc;                    // staged weights of the current round
+    ast_project2d_stats st;
+    StageTimer *tk;
+    int sm_count;
+};
+
+// index work of one round: pairs [w0, w1) of the combined emit order -- tiled pairs [0, T), then the pairs of the current
+// large-h window [base, base + HP): emit, stable sort by tile key, pair records, tile ranges, work items.
+static int prep_round(Run2 &R, uint64_t w0, uint64_t w1, uint64_t T, uint64_t base, uint64_t HP, uint32_t n_hent, uint32_t *seg_target)
+{
+    const ast_project2d_params *p = R.p;
+    const Layout2 &L = R.L;
+    RoundSet S = L.set;
+    cudaStream_t q = R.s;
+    const int64_t nw = (int64_t)(w1 - w0);
+    R.tk->begin(2);
+    if (w0 < T) {
+        emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, q>>>(R.a, L.block_pairs, L.block_huge, w0, w1 < T ? w1 : T, L.pairs_a, L.huge, 0, 0);
+        R.st.n_launches += 1;
+    }
+    if (HP > 0 && w1 > base) {
+        huge_tiles_kernel<true><<<(n_hent + 7) / 8, 256, 0, q>>>(R.a, L.huge, n_hent, L.hoff, base, w0, w1, L.pairs_a);
+        R.st.n_launches += 1;
+    }
+    R.tk->end();
+    int in_b = 0, nl = 0;
+    const int key_bits = ceil_log2_u64((uint64_t)L.ntiles) + R.a.img_shift;
+    R.tk->begin(3);
+    AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32, key_bits, L.sort_ws, q, &in_b, &nl));
+    R.tk->end();
+    R.st.n_launches += nl;
+    R.tk->begin(4);
+    AST_CUDA_TRY(cudaMemsetAsync(S.tbeg, 0, sizeof(uint32_t) * L.ntiles, q));
+    AST_CUDA_TRY(cudaMemsetAsync(S.tend, 0, sizeof(uint32_t) * L.ntiles, q));
+    Acc c = R.c;
+    c.sorted = in_b ? L.pairs_b : L.pairs_a;
+    S.pc = R.pc = reinterpret_cast<float2 *>(in_b ? L.pairs_a : L.pairs_b);      // 8 bytes per pair, like the pairs
+    const unsigned nbk = (unsigned)((nw + 255) / 256);
+#define AST_LAUNCH_PR(SH) do { if (p->n_prop == 1) pair_record_kernel<SH, 1><<<nbk, 256, 0, q>>>(c, nw, S.tbeg, S.tend, S.pp, S.pc); \
+                               else pair_record_kernel<SH, 2><<<nbk, 256, 0, q>>>(c, nw, S.tbeg, S.tend, S.pp, S.pc); } while (0)
+    if (R.a.shape == SHAPE_CUBIC) AST_LAUNCH_PR(SHAPE_CUBIC);
+    else if (R.a.shape == SHAPE_WENDLAND) AST_LAUNCH_PR(SHAPE_WENDLAND);
+    else AST_LAUNCH_PR(SHAPE_TABLE);
+#undef AST_LAUNCH_PR
+    *seg_target = segment_target(nw, (int64_t)R.sm_count * 4);
+    tile_segments_kernel<<<(unsigned)((L.ntiles + 1 + 255) / 256), 256, 0, q>>>(S.tbeg, S.tend, 0u, *seg_target, (int)L.ntiles, S.seg_off);
+    nl = 0;
+    AST_CUDA_TRY(scan_exclusive<uint32_t>(S.seg_off, L.ntiles + 1, S.seg_tmp, nullptr, q, &nl));
+    R.st.n_launches += 2 + nl;
+    R.tk->end();
+    AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
+}
+
+static int accumulate_round(Run2 &R, int64_t nw, uint32_t seg_target)
+{
+    const Layout2 &L = R.L;
+    const RoundSet &S = L.set;
+    Acc c = R.c;
+    c.sorted = nullptr;
+    c.tbeg = S.tbeg; c.tend = S.tend; c.pp = S.pp; c.pc = R.pc; c.seg_off = S.seg_off; c.seg_target = seg_target;
+    const int64_t max_items = L.ntiles + nw / (int64_t)seg_target;      // sum_t max(1, ceil(cnt_t / target)) <= this
+    R.tk->begin(5);
+    if (R.a.shape == SHAPE_CUBIC) launch_accum<SHAPE_CUBIC>(R.p->n_prop, c, max_items, R.s);
+    else if (R.a.shape == SHAPE_WENDLAND) launch_accum<SHAPE_WENDLAND>(R.p->n_prop, c, max_items, R.s);
+    else launch_accum<SHAPE_TABLE>(R.p->n_prop, c, max_items, R.s);
+    R.tk->end();
+    R.st.n_launches += 1;
+    AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
+}
+
+}  // namespace
+
 extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, const double *h, const double *const *prop,
                              double *out, void *workspace, size_t workspace_bytes, void *stream, ast_project2d_stats *stats)
 {
@@ -930,25 +934,34 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     AST_REQUIRE(out != nullptr, "out is null");
     AST_REQUIRE(p->n == 0 || (pos && h && prop), "null input pointer");
     for (int k = 0; k < p->n_prop && p->n > 0; ++k) AST_REQUIRE(prop[k] != nullptr, "prop[%d] is null", k);
-    Layout2 L = layout2(p, workspace);
+    Run2 R;
+    R.p = p;
+    R.L = layout2(p, workspace);
+    const Layout2 &L = R.L;
     if (workspace == nullptr || workspace_bytes < L.bytes) {
         set_error("workspace too small: need %zu bytes, have %zu", L.bytes, workspace_bytes);
         return AST_EWORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    StageTimer tm((p->flags & AST_FLAG_TIMING) != 0, s);
-    ast_project2d_stats st;
-    memset(&st, 0, sizeof st);
-    P2 a = make_p2(p, pos, h, prop, out);
-    a.pcount = L.pcount; a.pmask = L.pmask;
+    const bool timing = (p->flags & AST_FLAG_TIMING) != 0;
+    StageTimer tm(timing, s);
+    StageTimer tk(timing, s);
+    R.tk = &tk;
+    R.s = s;
+    memset(&R.st, 0, sizeof R.st);
+    ast_project2d_stats &st = R.st;
+    R.a = make_p2(p, pos, h, prop, out);
+    P2 &a = R.a;
+    a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp;
+    { int dev = 0; R.sm_count = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&R.sm_count, cudaDevAttrMultiProcessorCount, dev); }
 
     tm.begin(7);
-    StageTimer tk((p->flags & AST_FLAG_TIMING) != 0, s);
     tk.begin(6);
     if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * a.map_stride * p->n_prop, s));
     // entries 0..nb-1 are written by the binning kernels; only the sentinel entry nb (-> the totals after the scan) is zeroed
     AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs + L.nb, 0, sizeof(uint64_t), s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge + L.nb, 0, sizeof(uint64_t), s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.wexp, 0x80, sizeof(int) * AST_MAX_PROPS, s));          // = -2139062144: below any exponent
     tk.end();
     uint64_t totals[2] = { 0, 0 };
     if (p->n > 0) {
@@ -958,19 +971,15 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             // block (and everything, when AST_BIN_TMA=0 or a pointer is misaligned) through the plain kernel
             bool aligned = ((uintptr_t)pos % 16 == 0) && ((uintptr_t)h % 16 == 0);
             for (int k = 0; k < p->n_prop; ++k) aligned = aligned && ((uintptr_t)prop[k] % 16 == 0);
-            static int use_tma = -1;
-            if (use_tma < 0) { const char *e = getenv("AST_BIN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+            static const bool use_tma = env_flag("AST_BIN_TMA", true);
             const int64_t n_full = (aligned && use_tma) ? p->n / kBinThreads : 0;
             if (n_full > 0) {
-                int dev = 0, sm = 148;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
                 // persistent grid: one wave of resident CTAs (multiple of the SM count)
 #define AST_LAUNCH_TMA(SH, NPV, PERV)                                                                                       \
     do {                                                                                                                \
         int per_sm = 1;                                                                                                 \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_tma_kernel<SH, NPV, PERV>, kBinThreads, 0);          \
-        int64_t grid = (int64_t)sm * (per_sm > 0 ? per_sm : 1);                                                         \
+        int64_t grid = (int64_t)R.sm_count * (per_sm > 0 ? per_sm : 1);                                                 \
         if (grid > n_full) grid = n_full;                                                                               \
         bin_tma_kernel<SH, NPV, PERV><<<(unsigned)grid, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full); \
     } while (0)
@@ -1011,92 +1020,68 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaStreamSynchronize(s));
     }
-    st.n_pairs = (int64_t)totals[0];
-    st.n_huge = (int64_t)totals[1];
-    if (totals[1] > (uint64_t)L.huge_cap) {
-        set_error("huge_capacity too small: need %llu entries, have %lld", (unsigned long long)totals[1], (long long)L.huge_cap);
+    const uint64_t T = totals[0], H = totals[1];
+    st.n_pairs = (int64_t)T;
+    st.n_huge = (int64_t)H;
+    if (T + H > 0 && p->pair_capacity <= 0) {
+        // nothing was deposited by the tile path yet, but the direct deposits of K1 are in `out`: the header documents it
+        set_error("pair_capacity is 0 but %llu pairs and %llu large-h particles need the tile path", (unsigned long long)T,
+                  (unsigned long long)H);
         if (stats) *stats = st;
         return AST_EWORKSPACE;
     }
-    if (totals[0] > 0 && p->pair_capacity <= 0) {
-        set_error("pair_capacity is 0 but %llu pairs are needed", (unsigned long long)totals[0]);
-        if (stats) *stats = st;
-        return AST_EWORKSPACE;
-    }
-    if (totals[0] + totals[1] > 0) {
-        const uint64_t cap = (uint64_t)L.pair_cap;
-        const int64_t rounds = totals[0] ? (int64_t)((totals[0] + cap - 1) / cap) : 1;
-        const int key_bits = ceil_log2_u64((uint64_t)L.ntiles) + a.img_shift;
-        Acc c;
-        c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
+    if (T + H > 0) {
+        Acc &c = R.c;
+        memset(&c, 0, sizeof c);
+        c.rec = L.rec; c.out = out;
         c.x_min = a.ax.vmin; c.y_min = a.ay.vmin; c.dx = a.ax.d; c.dy = a.ay.d; c.inv_dx = a.ax.inv_d; c.inv_dy = a.ay.inv_d;
         c.nx = p->nx; c.ny = p->ny; c.ntx = a.ntx; c.nty = a.nty; c.img_shift = a.img_shift;
         c.n_img = a.n_img; c.box_a = a.box_a; c.box_b = a.box_b; c.tab = a.tab;
-        c.map_stride = a.map_stride;
-        for (int64_t r = 0; r < rounds; ++r) {
-            const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
-            const int64_t nw = (int64_t)(w1 - w0);
-            tk.begin(2);
-            emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.block_pairs, L.block_huge, w0, w1, L.pairs_a, L.huge, r == 0,
-                                                              (uint64_t)L.huge_cap);
-            tk.end();
-            st.n_launches += 1;
-            int in_b = 0, nl = 0;
-            tk.begin(3);
-            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32, key_bits, L.sort_ws, s, &in_b, &nl));
-            tk.end();
-            st.n_launches += nl;
-            tk.begin(4);
-            AST_CUDA_TRY(cudaMemsetAsync(L.tbeg, 0, sizeof(uint32_t) * L.ntiles, s));
-            AST_CUDA_TRY(cudaMemsetAsync(L.tend, 0, sizeof(uint32_t) * L.ntiles, s));
-            c.sorted = in_b ? L.pairs_b : L.pairs_a;
-            c.pp = nullptr; c.pc = nullptr;
-            if (nw > 0) {
-                // staged pair records for the default accumulate kernel (AST_PAIR_RECORDS=0: gather inside the kernel instead);
-                // the weights go to the sort's free ping-pong buffer (8 bytes per pair, like the pairs)
-                static int use_records = -1;
-                if (use_records < 0) { const char *e = getenv("AST_PAIR_RECORDS"); use_records = (e && e[0] == '0') ? 0 : 1; }
-                const unsigned nbk = (unsigned)((nw + 255) / 256);
-                if (use_records && accum_variant() == 3) {
-                    float2 *pc = reinterpret_cast<float2 *>(in_b ? L.pairs_a : L.pairs_b);
-#define AST_LAUNCH_PR(SH) do { if (p->n_prop == 1) pair_record_kernel<SH, 1><<<nbk, 256, 0, s>>>(c, nw, L.tbeg, L.tend, L.pp, pc); \
-                               else pair_record_kernel<SH, 2><<<nbk, 256, 0, s>>>(c, nw, L.tbeg, L.tend, L.pp, pc); } while (0)
-                    if (a.shape == SHAPE_CUBIC) AST_LAUNCH_PR(SHAPE_CUBIC);
-                    else if (a.shape == SHAPE_WENDLAND) AST_LAUNCH_PR(SHAPE_WENDLAND);
-                    else AST_LAUNCH_PR(SHAPE_TABLE);
-#undef AST_LAUNCH_PR
-                    c.pp = L.pp; c.pc = pc;
-                } else {
-                    tile_range_kernel<<<nbk, 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
-                }
-                st.n_launches += 1;
-            }
-            c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
-            // work items: balanced segments of the tile lists
-            {
-                static int sm_count = 0;
-                if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-                c.seg_off = L.seg_off; c.seg_target = segment_target(nw, (int64_t)sm_count * 4); c.ntiles = (int)L.ntiles;
-                tile_segments_kernel<<<(unsigned)((L.ntiles + 1 + 255) / 256), 256, 0, s>>>(L.tbeg, L.tend, c.n_huge, c.seg_target,
-                                                                                        (int)L.ntiles, L.seg_off);
+        c.map_stride = a.map_stride; c.ntiles = (int)L.ntiles; c.wexp = L.wexp; c.n_huge = 0u;
+
+        int rc2 = AST_OK;
+        int64_t round_no = 0;
+        const uint64_t hcap = (uint64_t)L.huge_cap;
+        const uint64_t n_hwin = H ? (H + hcap - 1) / hcap : 1;
+        for (uint64_t hw = 0; hw < n_hwin && rc2 == AST_OK; ++hw) {
+            // ---- the large-h window: list entries [h0, h1) -> member-tile counts -> offsets (all on the caller's stream)
+            uint64_t HP = 0;
+            uint32_t n_hent = 0;
+            if (H) {
+                const uint64_t h0 = hw * hcap, h1 = (h0 + hcap < H) ? h0 + hcap : H;
+                n_hent = (uint32_t)(h1 - h0);
+                tk.begin(2);
+                emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, 0, L.pairs_a, L.huge, h0, h1);
+                AST_CUDA_TRY(cudaMemsetAsync(L.hoff + n_hent, 0, sizeof(uint64_t), s));
+                huge_tiles_kernel<false><<<(n_hent + 7) / 8, 256, 0, s>>>(a, L.huge, n_hent, L.hoff, 0, 0, 0, nullptr);
                 int nl = 0;
-                AST_CUDA_TRY(scan_exclusive<uint32_t>(L.seg_off, L.ntiles + 1, L.seg_tmp, nullptr, s, &nl));
-                st.n_launches += 1 + nl;
+                AST_CUDA_TRY(scan_exclusive<uint64_t>(L.hoff, (int64_t)n_hent + 1, L.hoff_tmp, nullptr, s, &nl));
+                st.n_launches += 2 + nl;
+                tk.end();
+                AST_CUDA_TRY(cudaMemcpyAsync(&HP, L.hoff + n_hent, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+                AST_CUDA_TRY(cudaStreamSynchronize(s));
+                st.n_pairs += (int64_t)HP;
             }
-            tk.end();
-            const int64_t max_items = L.ntiles + nw / (int64_t)c.seg_target;      // sum_t max(1, ceil(cnt_t / target)) <= this
-            tk.begin(5);
-            if (a.shape == SHAPE_CUBIC) launch_accum<SHAPE_CUBIC>(p->n_prop, c, max_items, s);
-            else if (a.shape == SHAPE_WENDLAND) launch_accum<SHAPE_WENDLAND>(p->n_prop, c, max_items, s);
-            else launch_accum<SHAPE_TABLE>(p->n_prop, c, max_items, s);
-            tk.end();
-            st.n_launches += 1;
-            AST_CUDA_TRY(cudaGetLastError());
+            const uint64_t base = hw == 0 ? T : 0, total = base + HP;
+            if (total == 0) continue;
+            // rounds over the combined pair order
+            const uint64_t win = (uint64_t)L.win;
+            const uint64_t rounds = (total + win - 1) / win;
+            uint64_t per_round = rounds > 1 ? (((total + rounds - 1) / rounds + 8191ull) & ~8191ull) : win;   // even rounds
+            if (per_round > win) per_round = win;
+            for (uint64_t r = 0; r * per_round < total && rc2 == AST_OK; ++r, ++round_no) {
+                const uint64_t w0 = r * per_round, w1 = (w0 + per_round < total) ? w0 + per_round : total;
+                uint32_t seg_target = 1024;
+                rc2 = prep_round(R, w0, w1, hw == 0 ? T : 0, base, HP, n_hent, &seg_target);
+                if (rc2) break;
+                rc2 = accumulate_round(R, (int64_t)(w1 - w0), seg_target);
+            }
         }
-        st.n_rounds = rounds;
+        st.n_rounds = round_no;
+        if (rc2) { if (stats) *stats = st; return rc2; }
     }
     tm.end();
-    if (p->flags & AST_FLAG_TIMING) {
+    if (timing) {
         float total_ms[8];
         tk.collect(st.stage_ms, 8);
         tm.collect(total_ms, 8);
@@ -1120,8 +1105,11 @@ extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const
     }
     cudaStream_t s = (cudaStream_t)stream;
     P2 a = make_p2(p, pos, h, nullptr, nullptr);
-    a.pcount = L.pcount; a.pmask = L.pmask;
+    a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp;
+    uint64_t *pa = L.pairs_a, *pb = L.pairs_b;
+    const int64_t cap = L.win;
     uint64_t totals[2] = { 0, 0 };
+    uint64_t HP = 0;
     AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
     if (p->n > 0) {
@@ -1134,25 +1122,39 @@ extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaStreamSynchronize(s));
     }
-    if (counts) { counts[0] = (int64_t)totals[0]; counts[1] = (int64_t)totals[1]; }
-    if (totals[0] > (uint64_t)p->pair_capacity || totals[1] > (uint64_t)p->huge_capacity) {
-        set_error("capacity too small: need %llu pairs and %llu huge entries", (unsigned long long)totals[0],
-                  (unsigned long long)totals[1]);
+    const uint64_t T = totals[0], H = totals[1];
+    if (H > (uint64_t)L.huge_cap) {
+        if (counts) { counts[0] = (int64_t)T; counts[1] = (int64_t)H; }
+        set_error("capacity too small: need %llu huge entries", (unsigned long long)H);
         return AST_EWORKSPACE;
     }
-    if (totals[0] + totals[1] > 0) {
-        emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, totals[0], L.pairs_a, L.huge, 1,
-                                                          (uint64_t)L.huge_cap);
+    if (H > 0) {
+        const uint32_t nh = (uint32_t)H;
+        emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, 0, pa, L.huge, 0, H);
+        AST_CUDA_TRY(cudaMemsetAsync(L.hoff + nh, 0, sizeof(uint64_t), s));
+        huge_tiles_kernel<false><<<(nh + 7) / 8, 256, 0, s>>>(a, L.huge, nh, L.hoff, 0, 0, 0, nullptr);
+        AST_CUDA_TRY(scan_exclusive<uint64_t>(L.hoff, (int64_t)nh + 1, L.hoff_tmp, nullptr, s));
+        AST_CUDA_TRY(cudaMemcpyAsync(&HP, L.hoff + nh, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    const uint64_t total = T + HP;
+    if (counts) { counts[0] = (int64_t)total; counts[1] = (int64_t)H; }
+    if (total > (uint64_t)p->pair_capacity || total > (uint64_t)cap) {
+        set_error("capacity too small: need %llu pairs and %llu huge entries", (unsigned long long)total, (unsigned long long)H);
+        return AST_EWORKSPACE;
+    }
+    if (total + H > 0) {
+        if (T > 0) emit_kernel<<<(unsigned)L.nb, kBinThreads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, T, pa, L.huge, 0, 0);
+        if (HP > 0) huge_tiles_kernel<true><<<((uint32_t)H + 7) / 8, 256, 0, s>>>(a, L.huge, (uint32_t)H, L.hoff, T, 0, total, pa);
         AST_CUDA_TRY(cudaGetLastError());
-        if (pairs_emit && totals[0])
-            AST_CUDA_TRY(cudaMemcpyAsync(pairs_emit, L.pairs_a, sizeof(uint64_t) * totals[0], cudaMemcpyDeviceToDevice, s));
-        if (huge && totals[1]) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * totals[1], cudaMemcpyDeviceToDevice, s));
-        if (pairs_sorted && totals[0]) {
+        if (pairs_emit && total)
+            AST_CUDA_TRY(cudaMemcpyAsync(pairs_emit, pa, sizeof(uint64_t) * total, cudaMemcpyDeviceToDevice, s));
+        if (huge && H) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, s));
+        if (pairs_sorted && total) {
             int in_b = 0;
             const int key_bits = ceil_log2_u64((uint64_t)L.ntiles) + a.img_shift;
-            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, (int64_t)totals[0], 32, key_bits, L.sort_ws, s, &in_b));
-            AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? L.pairs_b : L.pairs_a, sizeof(uint64_t) * totals[0],
-                                         cudaMemcpyDeviceToDevice, s));
+            AST_CUDA_TRY(radix_sort_u64(pa, pb, (int64_t)total, 32, key_bits, L.sort_ws, s, &in_b));
+            AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? pb : pa, sizeof(uint64_t) * total, cudaMemcpyDeviceToDevice, s));
         }
     }
     AST_CUDA_TRY(cudaStreamSynchronize(s));

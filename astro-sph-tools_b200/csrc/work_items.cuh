@@ -58,8 +58,8 @@ __device__ __forceinline__ bool resolve_work(const A &a, TileWork &w)
 // overrides the default 32: measured at config 2 of the 2-D path, 35.1 ms un-split, 34.4 / 34.0 / 33.9 ms at 16 / 32 / 128 waves)
 inline uint32_t segment_target(int64_t n_pairs, int64_t slots)
 {
-    static int waves = 0;
-    if (waves == 0) { const char *e = getenv("AST_SEG_WAVES"); waves = e ? atoi(e) : 32; if (waves < 1) waves = 1; }
+    static const int waves_env = [] { const char *e = getenv("AST_SEG_WAVES"); const int w = e ? atoi(e) : 32; return w < 1 ? 1 : w; }();
+    const int waves = waves_env;
     int64_t target = (n_pairs / (slots * waves) + 31) & ~(int64_t)31;
     return (uint32_t)(target < 1024 ? 1024 : (target > 65536 ? 65536 : target));
 }

@@ -116,6 +116,24 @@ class ArrayReorder:
         return forwards
 
 
+def gather_rows_device(rows: np.ndarray, index: np.ndarray, default_value=None) -> np.ndarray:
+    """rows[index] on the GPU (ast_gather_rows); rows of the result whose index is negative take default_value"""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = np.ascontiguousarray(rows)
+    out_host = np.empty((index.shape[0],) + rows.shape[1:], dtype=rows.dtype)
+    if default_value is not None:
+        out_host[...] = default_value
+    row_bytes = rows.dtype.itemsize * int(np.prod(rows.shape[1:], dtype=np.int64))
+    src = torch.from_numpy(rows.view(np.uint8).reshape(-1)).to(dev)
+    out = torch.from_numpy(out_host.view(np.uint8).reshape(-1)).to(dev)
+    idx = torch.from_numpy(np.ascontiguousarray(index, dtype=np.int64)).to(dev)
+    _lib.check(lib.ast_gather_rows(_lib.ptr(src), C.c_int64(row_bytes), _lib.ptr(idx), C.c_int64(index.shape[0]), _lib.ptr(out),
+                                   _lib.stream_ptr()))
+    return out.cpu().numpy().view(rows.dtype).reshape(out_host.shape)
+
+
 def match_ids(source_ids, target_ids, source_filter=None, target_filter=None) -> np.ndarray:
     """For every target ID the index of the equal source ID, -1 where there is none (GPU hash join)."""
     return _match(np.asarray(source_ids), np.asarray(target_ids), source_filter, target_filter)

@@ -5,6 +5,7 @@ C ABI (include/astro_sph_b200.h: ast_project2d).  PyTorch is used for device mem
 many maps of one snapshot) do not reallocate.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -52,6 +53,7 @@ class Projector2D:
         self.huge_min_tiles = int(huge_min_tiles)
         self._ws = None
         self.last_stats = None
+        self._lock = threading.RLock()        # one workspace and one set of staging buffers: calls on this engine serialise
 
     # ---- parameters -------------------------------------------------------------------------------------
     def _set_kernel(self, p, kernel):
@@ -126,17 +128,12 @@ class Projector2D:
             raise ValueError("out must be a contiguous float64 tensor of n_prop*nx*ny elements")
         prop_ptrs = (C.c_void_p * _lib.MAX_PROPS)(*[q.data_ptr() for q in plist] + [None] * (_lib.MAX_PROPS - len(plist)))
         stats = _lib.Project2DStats()
-        with torch.cuda.device(self.device):
-            while True:
-                ws = self._workspace(p)
-                rc = self.lib.ast_project2d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), prop_ptrs, _lib.ptr(out), _lib.ptr(ws),
-                                            C.c_size_t(ws.numel()), _lib.stream_ptr(stream), C.byref(stats))
-                if rc == _lib.AST_EWORKSPACE and stats.n_huge > p.huge_capacity:
-                    self.huge_capacity = int(stats.n_huge * 1.25) + 1024     # grow the large-h list and retry
-                    p.huge_capacity = self.huge_capacity
-                    continue
-                _lib.check(rc)
-                break
+        with torch.cuda.device(self.device), self._lock:
+            # pair_capacity and huge_capacity only size windows: the library walks any number of pairs / large-h entries
+            # through them in rounds and never fails for lack of capacity once it has started depositing
+            ws = self._workspace(p)
+            _lib.check(self.lib.ast_project2d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), prop_ptrs, _lib.ptr(out), _lib.ptr(ws),
+                                              C.c_size_t(ws.numel()), _lib.stream_ptr(stream), C.byref(stats)))
         self.last_stats = dict(n_pairs=stats.n_pairs, n_huge=stats.n_huge, n_rounds=stats.n_rounds,
                                n_launches=stats.n_launches, stage_ms=list(stats.stage_ms))
         out = out.view(len(plist), p.nx, p.ny)
@@ -159,8 +156,9 @@ class Projector2D:
         if nb == 1:
             # float32 host arrays (the ingestion shim's opt-in) cross PCIe as float32 and are widened on the device: exact
             to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True).to(torch.float64)
-            pos_d, h_d = to_dev(positions), to_dev(smoothing_lengths)
-            props_d = [to_dev(q) for q in plist]
+            with torch.cuda.device(dev), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
+                pos_d, h_d = to_dev(positions), to_dev(smoothing_lengths)      # uploads ordered on the stream that computes
+                props_d = [to_dev(q) for q in plist]
             out = self.project(pos_d, h_d, props_d[0] if single else props_d, image_size, axis, bounds, kernel, periodic, box,
                                stream=stream)
         else:
@@ -169,7 +167,7 @@ class Projector2D:
             plist = [np.ascontiguousarray(q) for q in plist]
             bn, cuts = batch_cuts(n, nb, ramp)
             nb = len(cuts) - 1
-            with torch.cuda.device(dev):
+            with torch.cuda.device(dev), self._lock:
                 compute = stream if stream is not None else torch.cuda.current_stream()
                 if getattr(self, "_copy_stream", None) is None:
                     self._copy_stream = torch.cuda.Stream(device=dev)
@@ -220,5 +218,7 @@ class Projector2D:
         # device -> pinned host block (from torch's caching host allocator, so no page faults and full PCIe rate); the
         # numpy array returned is a view that owns the block, i.e. a fresh array for the caller like the reference's
         host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-        host.copy_(out)
+        with torch.cuda.device(dev), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
+            host.copy_(out, non_blocking=True)                               # ordered behind the deposition on ITS stream
+            torch.cuda.current_stream().synchronize()
         return host.numpy()

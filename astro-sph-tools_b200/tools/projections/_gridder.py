@@ -3,6 +3,7 @@ function, so the rules are those of its 2-D pixel routine (tools/projections/_pi
 carried to three axes: grid[xi,yi,zi] = sum_i A_i W(|p_i - corner(xi,yi,zi)|, h_i) over r^2 < (2 h_i)^2 with
 corner = min + index*delta.  Arguments follow create_image's style (reference _projector.py:75-87)."""
 import ctypes as C
+import threading
 from typing import Callable
 
 import numpy as np
@@ -26,6 +27,7 @@ class Gridder3D:
         self.huge_min_bricks = int(huge_min_bricks)
         self._ws = None
         self.last_stats = None
+        self._lock = threading.RLock()        # one workspace: calls on this engine serialise
 
     def params(self, n, grid_size, lo, hi, kernel, periodic=False, box=None, timing=False, accumulate=False):
         p = _lib.Grid3DParams()
@@ -81,7 +83,7 @@ class Gridder3D:
         if out is None:
             out = torch.empty((p.nx, p.ny, p.nz), dtype=torch.float64, device=self.device)
         stats = _lib.Project2DStats()
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), self._lock:
             while True:
                 ws = self.workspace(p)
                 rc = self.lib.ast_grid3d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), _lib.ptr(prop), _lib.ptr(out), _lib.ptr(ws),

@@ -9,6 +9,7 @@ non-periodic, K = 32 hard-coded (``N_NABOURS``, :63, with a TODO to make it a se
 Distances are bit-equal to scipy's float64 arithmetic.  CUDA only (ast_knn_h); no CPU fallback.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -27,6 +28,7 @@ class SmoothingLengthSolver:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.cell_target = float(cell_target)
         self._ws = None
+        self._lock = threading.RLock()        # one workspace: calls on this solver serialise
 
     def solve(self, pos, k=DEFAULT_K, box_size=None, q_begin=0, q_count=0, want_neighbours=False, want_distances=False,
               stream=None, kernel="lockstep", full_build=False):
@@ -54,13 +56,13 @@ class SmoothingLengthSolver:
         nq = int(q_count) if q_count and q_count > 0 else n
         need = C.c_size_t(0)
         _lib.check(self.lib.ast_knn_workspace_bytes(C.byref(p), C.byref(need)))
-        if self._ws is None or self._ws.numel() < need.value:
-            self._ws = None
-            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
         h = torch.empty(nq, dtype=torch.float64, device=self.device)
         idx = torch.empty((nq, k), dtype=torch.int32, device=self.device) if want_neighbours else None
         dist = torch.empty((nq, k), dtype=torch.float64, device=self.device) if want_distances else None
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), self._lock:
+            if self._ws is None or self._ws.numel() < need.value:
+                self._ws = None
+                self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
             _lib.check(self.lib.ast_knn_h(C.byref(p), _lib.ptr(pos), _lib.ptr(h), _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(self._ws),
                                           C.c_size_t(self._ws.numel()), _lib.stream_ptr(stream)))
         out = (h,)
@@ -107,7 +109,7 @@ class SmoothingLengthSolver:
         m = queries.shape[0]
         dist = torch.empty((m, k), dtype=torch.float64, device=self.device)
         idx = torch.empty((m, k), dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), self._lock:
             _lib.check(self.lib.ast_knn_query(C.byref(p), _lib.ptr(data), _lib.ptr(queries), C.c_int64(m), _lib.ptr(dist), _lib.ptr(idx),
                                               _lib.ptr(self._ws), C.c_size_t(self._ws.numel()), _lib.stream_ptr(stream)))
         return dist, idx

@@ -114,3 +114,59 @@ def test_gather_positions_without_process_group():
     p = torch.zeros((5, 3), dtype=torch.float64)
     allp, off = gather_positions(p)
     assert allp is p and off == 0
+
+
+# ---- sharded ID matching (the reference's ArrayReorder_MPI_2 contract, tools/_ArrayReorder.py:88-258) -----------------------
+def _numpy_matcher(source_ids, target_ids, source_filter, target_filter):
+    """stand-in for the GPU hash join: index of the equal source element per target, -1 where there is none"""
+    order = np.argsort(source_ids, kind="stable")
+    pos = np.searchsorted(source_ids[order], target_ids)
+    pos[pos >= len(order)] = 0
+    hit = (source_ids[order][pos] == target_ids) if len(order) else np.zeros(len(target_ids), dtype=bool)
+    if target_filter is not None:
+        hit &= np.asarray(target_filter, dtype=bool)
+    return np.where(hit, order[pos] if len(order) else 0, -1).astype(np.int64)
+
+
+def _numpy_row_gather(rows, index, default):
+    out = np.empty((len(index),) + rows.shape[1:], dtype=rows.dtype)
+    if default is not None:
+        out[...] = default
+    out[index >= 0] = rows[index[index >= 0]]
+    return out
+
+
+def _reorder_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from astro_sph_tools_b200 import distributed as astd
+    from reorder_util import load_reorder
+    g = load_reorder("filters")                                           # golden case produced by the reference's own class
+    src, tgt, data = g["source_ids"], g["target_ids"], g["data"]
+    sf, tf = g["source_order_filter"], g["target_order_filter"]
+    s0, s1 = astd.shard_bounds(len(src), world, rank)
+    cut = (len(tgt) * 3) // 10                                            # unequal target shards
+    t0, t1 = (0, cut) if rank == 0 else (cut, len(tgt))
+    r = astd.ShardedArrayReorder.create(src[s0:s1], tgt[t0:t1], sf[s0:s1], tf[t0:t1], matcher=_numpy_matcher, row_gather=_numpy_row_gather)
+    out = r(data[s0:s1], default_value=g["default_value"])
+    q.put((rank, bool(np.array_equal(out, g["result"][t0:t1])), bool(np.array_equal(r.target_filter, g["target_filter"][t0:t1]))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_reorder_equals_the_reference_result_per_rank():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reorder_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = []
+    while not q.empty():
+        got.append(q.get())
+    assert sorted(g[0] for g in got) == [0, 1] and all(g[1] and g[2] for g in got)

@@ -6,22 +6,28 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def reference_reorder(source_order, target_order, source_data, default_value, source_filter=None, target_filter=None):
-    """the reference's arithmetic: argsort + np.isin membership filters + order conversion (lines 988-1032), then
-    output[dest_filter] = source_data[source_filter][order_conversion_indexes] (line 959)"""
-    sos, tos = source_order.argsort(), target_order.argsort()
-    sus, tus = sos.argsort(), tos.argsort()
-    t_search = target_order[tos] if target_filter is None else target_order[tos][target_filter[tos]]
-    s_search = source_order[sos] if source_filter is None else source_order[sos][source_filter[sos]]
-    fwd = np.isin(source_order[sos], t_search)[sus]
-    bwd = np.isin(target_order[tos], s_search)[tus]
-    if source_filter is not None: fwd &= source_filter
-    if target_filter is not None: bwd &= target_filter
-    sos2, tos2 = source_order[fwd].argsort(), target_order[bwd].argsort()
-    conv = sos2[tos2.argsort()]
-    out = np.full((len(target_order),) + source_data.shape[1:], default_value, dtype=source_data.dtype)
-    out[bwd] = source_data[fwd][conv]
-    return out, fwd, bwd
+from reorder_util import golden_reorder_cases, load_reorder, reference_reorder
+
+
+@pytest.mark.parametrize("name", golden_reorder_cases())
+def test_reorder_equals_the_reference_class_results(name):
+    """golden results of the reference's own ArrayReorder (oracle/gen_golden_reorder.py): forward call, filters, flags, reverse"""
+    from astro_sph_tools_b200.tools import ArrayReorder
+    g = load_reorder(name)
+    r = ArrayReorder.create(g["source_ids"], g["target_ids"], g["source_order_filter"], g["target_order_filter"])
+    assert np.array_equal(r.source_filter, g["source_filter"]) and np.array_equal(r.target_filter, g["target_filter"])
+    assert r.matched_items == g["matched"]
+    flags = [r.uses_all_inputs, r.all_outputs_matched, r.lossless, r.matches_are_reduction, r.results_are_expansion,
+             r.results_are_subset, r.results_are_superset]
+    assert np.array_equal(np.array(flags), g["flags"])
+    kw = {} if g["default_value"] is None else dict(default_value=g["default_value"])
+    out = r(g["data"], **kw)
+    assert out.dtype == g["result"].dtype and out.shape == g["result"].shape
+    assert np.array_equal(out[r.target_filter], g["result"][r.target_filter])
+    if g["default_value"] is not None:
+        assert np.array_equal(out, g["result"])
+    back = r.reverse(g["result"], default_value=g["reverse_default"][()])
+    assert np.array_equal(back, g["reverse_result"], equal_nan=True)
 
 
 @pytest.mark.parametrize("n_src,n_tgt", [(1000, 1000), (50000, 20000), (3, 70000), (200000, 200000)])

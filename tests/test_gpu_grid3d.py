@@ -104,3 +104,18 @@ def test_create_grid_host_api_and_rounds(oracle):
     check(g2, ref)
     empty, _ = gpu_grid(np.zeros((0, 3)), np.zeros(0), np.zeros(0), (8, 8, 8), (0, 0, 0), (1, 1, 1))
     assert not empty.any()
+
+
+def test_grid_against_the_literal_numpy_restatement():
+    """independent pin (tests/literal3d.py): the reference's per-pixel rule carried to three dimensions, one voxel at a time,
+    with the reference's own compiled kernel function when oracle/_ref travelled to this box"""
+    from literal3d import grid3d_literal
+    rng = np.random.default_rng(4)
+    pos = rng.uniform(-0.05, 1.05, (800, 3))
+    h = rng.choice([0.01, 0.03, 0.06, 0.15], 800)
+    prop = rng.normal(size=800)
+    size, lo, hi = (20, 17, 23), (0.0, 0.0, 0.1), (1.0, 0.9, 1.0)
+    ref = grid3d_literal(pos, h, prop, size, lo, hi)
+    for kw in ({}, dict(small_max_vox=1 << 40), dict(small_max_vox=1, huge_min_bricks=1 << 40), dict(small_max_vox=1, huge_min_bricks=0)):
+        g, _ = gpu_grid(pos, h, prop, size, lo, hi, **kw)
+        assert rel_l2(g, ref) <= 1e-5 and abs(g.sum() - ref.sum()) <= 1e-6 * np.abs(ref).sum()

@@ -1,0 +1,130 @@
+"""-m gpu: round-2 additions to the 2-D path, each against the CPU oracle --
+  * capacities never fail after the direct deposits have started (host batches + accumulate mode + tiny huge_capacity),
+  * weights far outside float32 range (the tile path stores mantissa + exponent, sums in units of 2^E),
+  * the large-h split (a warp per large-h particle image emits its (tile, particle) pairs) on a big image, against the
+    all-tiled path whose per-block pair counts exceed 2^20,
+  * any pair window gives the same map.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2, random_cloud
+from gpu_util import dev, gpu_project
+
+pytestmark = pytest.mark.gpu
+
+
+def check(img, ref, tol_l2=1e-5, tol_tot=1e-6):
+    assert img.shape == ref.shape
+    assert rel_l2(img, ref) <= tol_l2
+    assert abs(img.sum() - ref.sum()) <= tol_tot * np.abs(ref).sum()
+
+
+def mixed_cloud(seed, n, L=10.0):
+    """tiny (direct deposit), medium (tiled) and very large (large-h list) supports in one set"""
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(0, L, (n, 3))
+    h = rng.choice([0.004 * L, 0.02 * L, 0.05 * L, 0.2 * L], n, p=[0.4, 0.3, 0.2, 0.1])
+    prop = rng.uniform(0.5, 1.5, n)
+    return pos, h, prop
+
+
+def test_host_batches_with_tiny_huge_capacity_do_not_double_count(oracle):
+    """the direct deposits of the binning kernel used to be added twice when a batch in accumulate mode
+    overflowed huge_capacity and the call was retried.  Capacities are windows now: no retry, no failure."""
+    from astro_sph_tools_b200.tools.projections import Projector2D
+    pos, h, prop = mixed_cloud(3, 6000)
+    eng = Projector2D(huge_capacity=16, huge_min_tiles=4, pair_capacity=30000)
+    img = eng.project_host(pos, h, prop, (256, 256), 2, (0.0, 10.0, 0.0, 10.0), batch_particles=1500)
+    assert eng.last_stats["n_batches"] >= 4
+    ref = oracle.project2d(pos, h, prop, (256, 256), 2, 0.0, 10.0, 0.0, 10.0)
+    check(img, ref)
+    # one device call, accumulate=True on top of an existing map, same tiny windows
+    import torch
+    base = torch.full((256, 256), 3.0, dtype=torch.float64, device="cuda")
+    out = eng.project(dev(pos), dev(h), dev(prop), (256, 256), 2, (0.0, 10.0, 0.0, 10.0), out=base, accumulate=True)
+    st = eng.last_stats
+    assert st["n_huge"] > 16 and st["n_rounds"] > 4            # several large-h windows, several pair rounds each
+    check(out.cpu().numpy() - 3.0, ref)
+
+
+@pytest.mark.parametrize("scale", [1e45, 1e-60, 1e300])
+def test_weights_outside_float32_range(oracle, scale):
+    """a luminosity in erg/s times 1/(pi h^3) is ~1e48, Msun over cm^3 ~1e-59; the reference is float64"""
+    pos, h, prop = mixed_cloud(8, 3000)
+    ref = oracle.project2d(pos, h, prop, (192, 192), 2, 0.0, 10.0, 0.0, 10.0)
+    for kw in ({}, dict(small_max_px=1, huge_min_tiles=1 << 40), dict(small_max_px=1, huge_min_tiles=0)):
+        img, _ = gpu_project(pos, h, prop * scale, (192, 192), 2, (0.0, 10.0, 0.0, 10.0), **kw)
+        assert np.isfinite(img).all()
+        check(img / scale, ref)
+    # two fields of very different magnitude in one pass keep their own exponents
+    both, _ = gpu_project(pos, h, [prop * scale, prop * 1e-3], (192, 192), 2, (0.0, 10.0, 0.0, 10.0))
+    check(both[0] / scale, ref)
+    check(both[1] / 1e-3, ref)
+
+
+def test_zero_and_signed_weights_keep_their_sign_and_zero(oracle):
+    pos, h, _ = mixed_cloud(9, 2000)
+    prop = np.random.default_rng(1).normal(size=2000)
+    prop[::3] = 0.0
+    img, _ = gpu_project(pos, h, prop, (128, 128), 2, (0.0, 10.0, 0.0, 10.0), small_max_px=1)
+    ref = oracle.project2d(pos, h, prop, (128, 128), 2, 0.0, 10.0, 0.0, 10.0)
+    assert rel_l2(img, ref) <= 1e-5
+    zero, _ = gpu_project(pos, h, np.zeros(2000), (128, 128), 2, (0.0, 10.0, 0.0, 10.0), small_max_px=1)
+    assert not zero.any()
+
+
+def test_large_h_split_on_a_big_image(oracle):
+    """300 particles whose supports cover thousands of tiles of a 2048^2 map.  Default: they go through the warp-per-particle
+    split kernel.  huge_min_tiles = 2^40 forces them through the thread-per-particle enumeration, where one block of 256
+    particles holds > 2^20 pairs (the packed 20-bit block count used to overflow).  Same map either way."""
+    rng = np.random.default_rng(12)
+    n = 300
+    pos = rng.uniform(0.2, 0.8, (n, 3))
+    h = rng.uniform(0.12, 0.3, n)
+    prop = rng.uniform(0.5, 1.5, n)
+    size, b = (2048, 2048), (0.0, 1.0, 0.0, 1.0)
+    ref = oracle.project2d(pos, h, prop, size, 2, *b)
+    split, st = gpu_project(pos, h, prop, size, 2, b)
+    assert st["n_huge"] == n and st["n_pairs"] > (1 << 20)
+    check(split, ref)
+    tiled, st2 = gpu_project(pos, h, prop, size, 2, b, huge_min_tiles=1 << 40)
+    assert st2["n_huge"] == 0 and st2["n_pairs"] == st["n_pairs"]
+    check(tiled, ref)
+    # a mix: many ordinary particles plus a few large ones, periodic images on
+    pos2, h2, prop2 = mixed_cloud(5, 20000, L=1.0)
+    ref2 = oracle.project2d(pos2, h2, prop2, (512, 512), 2, *b, periodic=True, box=(1.0, 1.0))
+    img2, st3 = gpu_project(pos2, h2, prop2, (512, 512), 2, b, periodic=True, box=(1.0, 1.0), huge_min_tiles=16)
+    assert st3["n_huge"] > 1000
+    check(img2, ref2)
+
+
+def test_large_h_pairs_bit_exact(oracle):
+    """index work of the split: the pairs of the large-h entries follow the tiled pairs, entry by entry in list order, tiles
+    in emit order -- array_equal with the oracle, before and after the stable sort"""
+    from gpu_util import gpu_bin2d
+    pos, h, _ = mixed_cloud(21, 5000)
+    for periodic, box in ((False, None), (True, (10.0, 10.0))):
+        o = oracle.bin2d(pos, h, (320, 320), 2, 0.0, 10.0, 0.0, 10.0, tile=32, small_max_px=16, huge_min_tiles=6, periodic=periodic, box=box)
+        g = gpu_bin2d(pos, h, (320, 320), 2, (0.0, 10.0, 0.0, 10.0), periodic, box, 16, 6)
+        assert len(o["huge"]) > 300 and np.array_equal(g["huge"], o["huge"])
+        assert np.array_equal(g["pairs"], o["pairs"]) and np.array_equal(g["sorted"], o["sorted"])
+
+
+def test_rounds_over_a_small_pair_window_equal_one_round():
+    """any pair_capacity gives the same map: the pairs are walked through the window in rounds (random particle order, so every
+    round touches every tile)"""
+    import torch
+    from astro_sph_tools_b200 import synthetic
+    from astro_sph_tools_b200.tools.projections import Projector2D
+    s = synthetic.s1(64, k=48, h_mode="uniform")
+    perm = np.random.default_rng(2).permutation(len(s["h"]))
+    pos, h, m = dev(s["pos"][perm]), dev(s["h"][perm]), dev(s["mass"][perm])
+    args = ((512, 512), 2, (0.0, 1.0, 0.0, 1.0))
+    one = Projector2D()
+    a = one.project(pos, h, m, *args).clone()
+    many = Projector2D(pair_capacity=300_000)
+    b = many.project(pos, h, m, *args)
+    torch.cuda.synchronize()
+    assert one.last_stats["n_rounds"] == 1 and many.last_stats["n_rounds"] >= 7 and one.last_stats["n_pairs"] == many.last_stats["n_pairs"]
+    assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
