@@ -140,18 +140,26 @@ __device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double 
         dx2[k] = (i0 + k >= 0 && i0 + k < p.ax.n) ? AST_DMUL(tx_k, tx_k) : INFINITY;
         dy2[k] = (j0 + k >= 0 && j0 + k < p.ay.n) ? AST_DMUL(ty_k, ty_k) : INFINITY;
     }
+    // exact float64 mask for the four candidates first, then ONE deposit loop over the hits of this lane: with four separate
+    // predicated deposit blocks every block ran for the few lanes that hit that particular candidate (ncu: 22.8 of 32 lanes
+    // active over the kernel); here pass n serves the n-th hit of every lane that has one
+    float q2[4];
+    unsigned hit = 0u;
 #pragma unroll
-    for (int kx = 0; kx < 2; ++kx)
+    for (int c = 0; c < 4; ++c) {
+        const double r2 = AST_DADD(dx2[c >> 1], dy2[c & 1]);
+        q2[c] = (float)r2 * inv_h2;
+        hit |= (r2 < R2) ? (1u << c) : 0u;
+    }
+    while (hit) {
+        const int c = __ffs((int)hit) - 1;
+        hit &= hit - 1u;
+        const float s = (c & 2) ? ((c & 1) ? q2[3] : q2[2]) : ((c & 1) ? q2[1] : q2[0]);
+        const double f = (double)shape_eval<SHAPE>(fast_sqrt(s), p.tab);
+        double *o = p.out + (size_t)(i0 + (c >> 1)) * (size_t)p.ay.n + (size_t)(j0 + (c & 1));
 #pragma unroll
-        for (int ky = 0; ky < 2; ++ky) {
-            const double r2 = AST_DADD(dx2[kx], dy2[ky]);
-            if (r2 < R2) {
-                const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)r2 * inv_h2), p.tab);
-                double *o = p.out + (size_t)(i0 + kx) * (size_t)p.ay.n + (size_t)(j0 + ky);
-#pragma unroll
-                for (int k = 0; k < NP; ++k) atomicAdd(o + k * p.map_stride, coef[k] * f);
-            }
-        }
+        for (int k = 0; k < NP; ++k) atomicAdd(o + k * p.map_stride, coef[k] * f);
+    }
 }
 
 // per-particle body of K1: classification, pair / large-h counts, direct deposit, record
@@ -213,11 +221,9 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
             r.c[k] = 0.f;
             if (k < NP) split_weight(coef[k < NP ? k : 0], r.c[k], e);
             r.e[k] = (int16_t)e;
-            if (k < NP && e != kZeroExp) {                      // one atomic per warp and field: lanes with records agree on a maximum
-                const unsigned peers = __activemask();
-                const int emax = __reduce_max_sync(peers, e);
-                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicMax(p.wexp + k, emax);
-            }
+            // running maximum of the call: a plain (possibly stale) read settles it for all but the first few warps, the
+            // atomic only runs when this particle would raise it
+            if (k < NP && e != kZeroExp && e > __ldcg(p.wexp + k)) atomicMax(p.wexp + k, e);
         }
         rec[i] = r;
     }
@@ -292,18 +298,21 @@ struct __align__(128) BinStage {
     double prop[NP][kBinThreads];
 };
 
-template <int SHAPE, int NP, bool PER>
-__global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
-                                                              uint64_t *__restrict__ block_huge, int64_t n_full_blocks)
+// NSTAGE stages of 256 particles per CTA: NSTAGE - 1 bulk copies are in flight while one stage is worked on (a B200 needs
+// ~35 KB in flight per SM to cover HBM latency at full bandwidth; two stages of 10 KB on three resident CTAs were just short).
+template <int SHAPE, int NP, bool PER, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(kBinThreads, MINB) bin_tma_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
+                                                                    uint64_t *__restrict__ block_huge, int64_t n_full_blocks)
 {
-    __shared__ BinStage<NP> st[2];
-    __shared__ __align__(8) uint64_t bar[2];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BinStage<NP> *st = reinterpret_cast<BinStage<NP> *>(smem_raw);
+    __shared__ __align__(8) uint64_t bar[NSTAGE];
     __shared__ uint64_t red[34];
     const int tid = threadIdx.x;
     constexpr uint32_t kBytes = (uint32_t)sizeof(BinStage<NP>);
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+#pragma unroll
+        for (int k = 0; k < NSTAGE; ++k) mbar_init(&bar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -316,12 +325,17 @@ __global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restr
         for (int k = 0; k < NP; ++k) tma_load_1d(st[s].prop[k], p.prop[k] + i0, kBinThreads * 8, &bar[s]);
     };
     int64_t blk = blockIdx.x;
-    if (tid == 0 && blk < n_full_blocks) issue(blk, 0);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NSTAGE - 1; ++k)
+            if (blk + (int64_t)k * gridDim.x < n_full_blocks) issue(blk + (int64_t)k * gridDim.x, k);
+    }
     uint32_t phase_bits = 0u;                                   // bit s = parity to wait for on stage s (kept in a register)
-    for (int it = 0; blk < n_full_blocks; blk += gridDim.x, ++it) {
-        const int s = it & 1;
-        const int64_t next = blk + gridDim.x;
-        if (tid == 0 && next < n_full_blocks) issue(next, s ^ 1);     // stage s^1 was released by the barrier below
+    int s = 0;
+    for (; blk < n_full_blocks; blk += gridDim.x) {
+        // the stage worked on in the previous iteration was released by the barrier at its end: refill it
+        const int64_t ahead = blk + (int64_t)(NSTAGE - 1) * gridDim.x;
+        if (tid == 0 && ahead < n_full_blocks) issue(ahead, s == 0 ? NSTAGE - 1 : s - 1);
         mbar_wait(&bar[s], (phase_bits >> s) & 1u);
         phase_bits ^= 1u << s;
         const int64_t i = blk * kBinThreads + tid;
@@ -343,6 +357,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_tma_kernel(P2 p, Rec *__restr
             block_pairs[blk] = packed & ((1ull << 44) - 1ull);
             block_huge[blk] = packed >> 44;
         }
+        s = s + 1 == NSTAGE ? 0 : s + 1;
     }
 }
 
@@ -651,9 +666,14 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
                 for (int jj = 0; jj < NPIX; ++jj) { acc64[k][jj] += (double)acc[k][jj]; acc[k][jj] = 0.f; }
         }
     }
-    int wexp[NP];
+    // the sums are in units of 2^E_k: two exact power-of-two factors (E_k spans -1073 .. 1024, one factor could overflow)
+    double sc1[NP], sc2[NP];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) wexp[k] = max(a.wexp[k], -4000);
+    for (int k = 0; k < NP; ++k) {
+        const int e = min(max(a.wexp[k], -2040), 2040), e1 = e / 2, e2 = e - e1;
+        sc1[k] = __longlong_as_double((long long)(e1 + 1023) << 52);
+        sc2[k] = __longlong_as_double((long long)(e2 + 1023) << 52);
+    }
 #pragma unroll
     for (int ix = 0; ix < PX; ++ix) {
         const int xi = X0 + xl + ix;
@@ -665,7 +685,7 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 double *o = a.out + k * a.map_stride + (size_t)xi * a.ny + yi;
-                const double v = scalbn(acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy], wexp[k]);   // sums are in units of 2^E_k
+                const double v = (acc64[k][ix * PY + iy] + (double)acc[k][ix * PY + iy]) * sc1[k] * sc2[k];
                 if (w.atomic_out) atomicAdd(o, v); else *o += v;
             }
         }
@@ -975,13 +995,22 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             const int64_t n_full = (aligned && use_tma) ? p->n / kBinThreads : 0;
             if (n_full > 0) {
                 // persistent grid: one wave of resident CTAs (multiple of the SM count)
-#define AST_LAUNCH_TMA(SH, NPV, PERV)                                                                                       \
+#define AST_LAUNCH_TMA2(SH, NPV, PERV, NST, MB)                                                                            \
     do {                                                                                                                \
+        auto kern = bin_tma_kernel<SH, NPV, PERV, NST, MB>;                                                             \
+        const size_t smem = (size_t)NST * sizeof(BinStage<NPV>);                                                        \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         int per_sm = 1;                                                                                                 \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_tma_kernel<SH, NPV, PERV>, kBinThreads, 0);          \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBinThreads, smem);                                \
         int64_t grid = (int64_t)R.sm_count * (per_sm > 0 ? per_sm : 1);                                                 \
         if (grid > n_full) grid = n_full;                                                                               \
-        bin_tma_kernel<SH, NPV, PERV><<<(unsigned)grid, kBinThreads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full); \
+        kern<<<(unsigned)grid, kBinThreads, smem, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full);                  \
+    } while (0)
+#define AST_LAUNCH_TMA(SH, NPV, PERV)                                                                                   \
+    do {                                                                                                                \
+        static const int nst = env_int("AST_BIN_STAGES", 4), mb = env_int("AST_BIN_MINB", 3);                           \
+        if (nst <= 2) { if (mb >= 4) AST_LAUNCH_TMA2(SH, NPV, PERV, 2, 4); else AST_LAUNCH_TMA2(SH, NPV, PERV, 2, 3); }  \
+        else { if (mb >= 4) AST_LAUNCH_TMA2(SH, NPV, PERV, 4, 4); else AST_LAUNCH_TMA2(SH, NPV, PERV, 4, 3); }           \
     } while (0)
                 {
                     const bool per = a.n_img > 1;
@@ -993,6 +1022,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
 #undef AST_D2
                 }
 #undef AST_LAUNCH_TMA
+#undef AST_LAUNCH_TMA2
                 st.n_launches += 1;
             }
             const int64_t n_rest = L.nb - n_full;

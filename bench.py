@@ -537,6 +537,8 @@ def main():
             return dict(parity_of(crop, ref), window=f"{wp}^2 pixels of the timed map at [{lo:g},{hi:g})^2 vs oracle/sph_oracle.c fed the "
                                                     f"{int(sel.sum())} particles within 2 h_max of it"), t, int(sel.sum())
         parity, t_w, n_w = run_window(wp)
+        if not (parity["rel_l2"] <= 1e-5 and parity["total_rel"] <= 1e-6):
+            raise SystemExit(f"PARITY FAILURE: the timed map does not match the oracle: {parity}")      # no number without parity
         if world == 1 and not args.no_cpu_baseline:
             # bounded CPU sample: grow the window until the oracle runs for about cpu_target_s seconds
             rate = wp * wp / max(t_w, 1e-3)

@@ -170,3 +170,46 @@ def test_sharded_reorder_equals_the_reference_result_per_rank():
     while not q.empty():
         got.append(q.get())
     assert sorted(g[0] for g in got) == [0, 1] and all(g[1] and g[2] for g in got)
+
+
+# ---- slab + ghost-zone smoothing lengths ------------------------------------------------------------------
+def _slab_worker(rank, world, port, case, q):
+    import sys
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from astro_sph_tools_b200 import distributed as astd, synthetic
+    if case == "lattice_periodic":
+        pos, _ = synthetic.s1_positions(20); box = 1.0; k = 16
+    elif case == "clustered_periodic":
+        pos, _ = synthetic.s2_positions(6000, 1.0, n_haloes=4, seed=3); box = 1.0; k = 24
+    else:                                                                  # open box, random order, unequal shards
+        rng = np.random.default_rng(9); pos = rng.normal(size=(5000, 3)) * np.array([3.0, 1.0, 0.5]); box = None; k = 12
+    n = len(pos)
+    cut = (n * 2) // 5 if case == "open_unequal" else astd.shard_bounds(n, world, 0)[1]
+    lo, hi = (0, cut) if rank == 0 else (cut, n)
+    h, st = astd.smoothing_lengths_slabs(torch.from_numpy(pos[lo:hi].copy()), k, box, solver=_ScipySolver(), return_stats=True)
+    ref = oracle.knn_scipy(pos, k, box)[0]
+    q.put((rank, bool(np.array_equal(h.numpy(), ref[lo:hi])), st["iterations"], st["local_set"], n))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["lattice_periodic", "clustered_periodic", "open_unequal"])
+def test_slab_ghost_smoothing_lengths_equal_the_full_search(case):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = []
+    while not q.empty():
+        got.append(q.get())
+    assert sorted(g[0] for g in got) == [0, 1] and all(g[1] for g in got)
+    if case == "lattice_periodic":                                        # positions are NOT replicated: slab + ghosts only
+        assert all(g[3] < 0.95 * g[4] for g in got)

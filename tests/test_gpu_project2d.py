@@ -34,7 +34,7 @@ def test_golden_maps(name, path):
     if path == "all_direct":
         assert st["n_pairs"] == 0 and st["n_huge"] == 0
     if path == "all_global":
-        assert st["n_pairs"] == 0
+        assert st["n_huge"] > 0 and st["n_pairs"] > 0          # every tiled image goes through the large-h split kernel
 
 
 def test_create_image_drop_in_signature():

@@ -75,15 +75,15 @@ def test_zero_and_signed_weights_keep_their_sign_and_zero(oracle):
 
 
 def test_large_h_split_on_a_big_image(oracle):
-    """300 particles whose supports cover thousands of tiles of a 2048^2 map.  Default: they go through the warp-per-particle
+    """300 particles whose supports cover ~5000 tiles each of a 4096^2 map.  Default: they go through the warp-per-particle
     split kernel.  huge_min_tiles = 2^40 forces them through the thread-per-particle enumeration, where one block of 256
     particles holds > 2^20 pairs (the packed 20-bit block count used to overflow).  Same map either way."""
     rng = np.random.default_rng(12)
     n = 300
-    pos = rng.uniform(0.2, 0.8, (n, 3))
-    h = rng.uniform(0.12, 0.3, n)
+    pos = rng.uniform(0.35, 0.65, (n, 3))
+    h = rng.uniform(0.15, 0.175, n)
     prop = rng.uniform(0.5, 1.5, n)
-    size, b = (2048, 2048), (0.0, 1.0, 0.0, 1.0)
+    size, b = (4096, 4096), (0.0, 1.0, 0.0, 1.0)
     ref = oracle.project2d(pos, h, prop, size, 2, *b)
     split, st = gpu_project(pos, h, prop, size, 2, b)
     assert st["n_huge"] == n and st["n_pairs"] > (1 << 20)
