@@ -999,19 +999,18 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     do {                                                                                                                \
         auto kern = bin_tma_kernel<SH, NPV, PERV, NST, MB>;                                                             \
         const size_t smem = (size_t)NST * sizeof(BinStage<NPV>);                                                        \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         int per_sm = 1;                                                                                                 \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBinThreads, smem);                                \
         int64_t grid = (int64_t)R.sm_count * (per_sm > 0 ? per_sm : 1);                                                 \
         if (grid > n_full) grid = n_full;                                                                               \
         kern<<<(unsigned)grid, kBinThreads, smem, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full);                  \
     } while (0)
-#define AST_LAUNCH_TMA(SH, NPV, PERV)                                                                                   \
-    do {                                                                                                                \
-        static const int nst = env_int("AST_BIN_STAGES", 4), mb = env_int("AST_BIN_MINB", 3);                           \
-        if (nst <= 2) { if (mb >= 4) AST_LAUNCH_TMA2(SH, NPV, PERV, 2, 4); else AST_LAUNCH_TMA2(SH, NPV, PERV, 2, 3); }  \
-        else { if (mb >= 4) AST_LAUNCH_TMA2(SH, NPV, PERV, 4, 4); else AST_LAUNCH_TMA2(SH, NPV, PERV, 4, 3); }           \
-    } while (0)
+    // measured (benchmarks/bin_probe.py, 512^3 particles with sub-pixel supports; stages x CTAs per SM): 2 x 3 (80 registers)
+    // 1.581 ms, 4 x 3: 1.587, 2 x 4 (64 registers, no spills): 1.469, 4 x 4: 1.488, 2 x 5 (48 registers, spills): 1.608,
+    // 2 x 6: 2.000 -- occupancy, not pipeline depth, is what hides the latency here.  (With SPH-realistic supports the
+    // 64-register build costs 0.5 ms of a 284 ms step: 7.69 instead of 7.18 ms.)
+#define AST_LAUNCH_TMA(SH, NPV, PERV) AST_LAUNCH_TMA2(SH, NPV, PERV, 2, 4)
                 {
                     const bool per = a.n_img > 1;
 #define AST_D2(SH) do { if (p->n_prop == 1) { if (per) AST_LAUNCH_TMA(SH, 1, true); else AST_LAUNCH_TMA(SH, 1, false); } \

@@ -31,6 +31,6 @@ print("stages", os.environ.get("AST_BIN_STAGES"), "minb", os.environ.get("AST_BI
       "bin_ms", round(eng.last_stats["stage_ms"][0], 4), "sum", float(out.sum()) / npix ** 2)
 ''' % ROOT
 n = sys.argv[1] if len(sys.argv) > 1 else "512"
-for st, mb in (("2", "3"), ("4", "3"), ("2", "4"), ("4", "4")):
+for st, mb in (("2", "3"), ("2", "4"), ("2", "5"), ("2", "6"), ("4", "4")):
     env = dict(os.environ, AST_BIN_STAGES=st, AST_BIN_MINB=mb)
     subprocess.run([sys.executable, "-c", CHILD, n], env=env, check=False)
