@@ -43,7 +43,16 @@ struct P3 {
     // written by bin3_kernel for the blocks that have pairs or large-h entries, read by emit3_kernel (one enumeration there)
     uint32_t *pcount;                // pairs of particle i
     uint64_t *pmask;                 // bit m: image m is tiled, bit 27 + m: image m is on the large-h list
+    const int *wexp;                 // binary exponent E of the largest |prop * norm(h)| of the call + kExpBias3 (0: none); the
+                                     // brick path stores float32 weights relative to 2^E (see wexp3_kernel)
 };
+
+// The brick kernels work on float32 weights, the 2-D reference rules on float64 in any unit system (1e48 or 1e-59
+// are legitimate weights).  Rec3 has no room for a per-particle exponent, so one pre-pass takes the largest binary exponent E
+// of prop * norm(h) over the call (16 bytes per particle: 0.05 ms at 256^3 against a 70 ms step); records hold
+// prop * norm(h) * 2^-E <= 1 (weights more than 2^126 below the largest flush to zero), bricks sum in those units and multiply
+// by 2^E in float64 when they write.  The direct deposits of few-voxel particles use the float64 weight as before.
+constexpr int kExpBias3 = 1 << 20;
 
 
 // periodic image shift along axis c of image m (0 when there is a single image).  Computed arithmetically: a table in
@@ -60,6 +69,19 @@ __device__ __forceinline__ double norm3(const P3 &p, double h)
     const double ih = 1.0 / h;
     const double t = p.norm_c * ih * ih;
     return p.norm_dim == 3 ? t * ih : t;
+}
+
+__global__ void __launch_bounds__(256) wexp3_kernel(P3 p, int *__restrict__ wexp)
+{
+    int e = 0;                                                    // biased exponent, 0 = nothing seen
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double h = p.h[i];
+        if (!(h > 0.0 && 2.0 * h < INFINITY)) continue;
+        const double c = p.prop[i] * norm3(p, h);
+        if (c != 0.0 && fabs(c) < INFINITY) { int ex; frexp(c, &ex); e = max(e, ex + kExpBias3); }
+    }
+    e = __reduce_max_sync(0xffffffffu, e);
+    if ((threadIdx.x & 31) == 0 && e > 0) atomicMax(wexp, e);
 }
 
 template <int SHAPE>
@@ -124,7 +146,8 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
             Rec3 r;
             r.x = x0[0]; r.y = x0[1]; r.z = x0[2];
             r.inv_h = (float)(1.0 / h);
-            r.c = (float)(p.prop[i] * norm3(p, h));
+            const int e = __ldg(p.wexp);
+            r.c = (float)scalbn(p.prop[i] * norm3(p, h), e > 0 ? kExpBias3 - e : 0);          // relative to 2^E
             rec[i] = r;
         }
     }
@@ -140,13 +163,13 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
 __global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_t *__restrict__ pairs_excl,
                                                              const uint64_t *__restrict__ huge_excl, uint64_t w0, uint64_t w1,
                                                              uint64_t *__restrict__ pairs, uint64_t *__restrict__ huge,
-                                                             int write_huge, uint64_t huge_capacity)
+                                                             uint64_t h0, uint64_t h1)
 {
     __shared__ uint32_t sm[34];
     const uint64_t pbase = pairs_excl[blockIdx.x], pnext = pairs_excl[blockIdx.x + 1];
     const uint64_t hbase = huge_excl[blockIdx.x], hnext = huge_excl[blockIdx.x + 1];
     const bool any_pairs = pnext > pbase && pnext > w0 && pbase < w1;
-    const bool any_huge = write_huge && hnext > hbase;
+    const bool any_huge = hnext > hbase && hnext > h0 && hbase < h1;     // large-h entries with list index in [h0, h1) -> huge[gh - h0]
     if (!any_pairs && !any_huge) return;
     const int64_t i = (int64_t)blockIdx.x * kBin3Threads + threadIdx.x;
     // counts and image masks come from bin3_kernel: one enumeration of the bricks here, and only for the images that have any
@@ -168,13 +191,14 @@ __global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_
         const double q[3] = { AST_DADD(x0[0], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(x0[1], image_shift3(p.n_img, p.box, m, 1)), AST_DADD(x0[2], image_shift3(p.n_img, p.box, m, 2)) };
         Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
         if (b.cls == CLS_TILED) {
+            if (!any_pairs) continue;
             for_each_brick3<BRICK>(p.ax, q, R2, b, p.nb[1], p.nb[2], [&](uint32_t key) {
                 if (g >= w0 && g < w1)
                     pairs[g - w0] = ((uint64_t)((key << p.img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
                 ++g;
             });
         } else if (b.cls == CLS_HUGE) {
-            if (write_huge && gh < huge_capacity) huge[gh] = ((uint64_t)m << 32) | (uint64_t)(uint32_t)i;
+            if (gh >= h0 && gh < h1) huge[gh - h0] = ((uint64_t)m << 32) | (uint64_t)(uint32_t)i;
             ++gh;
         }
     }
@@ -203,6 +227,7 @@ struct Acc3 {
     ShapeTab tab;
     const uint32_t *seg_off;     // work items over the brick lists (work_items.cuh); ntiles = number of bricks
     int ntiles;
+    const int *wexp;             // the float32 weights are relative to 2^(wexp[0] - kExpBias3)
 };
 
 // One CTA per work item of a brick (a whole brick list, or an interleaved share of a long one), four autonomous warps (no CTA barrier): warp w owns the 4x4x8 column (x,y quadrant) of the brick and
@@ -313,11 +338,14 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
     }
     const int xi = X0 + xl, yi = Y0 + yl;
     if (xi < a.n[0] && yi < a.n[1]) {
+        // the sums are in units of 2^E: two exact power-of-two factors (one could overflow at the ends of the exponent range)
+        const int eb = a.wexp[0], e = eb > 0 ? min(max(eb - kExpBias3, -2040), 2040) : 0, e1 = e / 2, e2 = e - e1;
+        const double sc1 = __longlong_as_double((long long)(e1 + 1023) << 52), sc2 = __longlong_as_double((long long)(e2 + 1023) << 52);
         double *row = a.out + ((size_t)xi * a.n[1] + yi) * a.n[2];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (Z0 + zl + k < a.n[2]) {
-                const double v = acc64[k] + (double)acc[k];
+                const double v = (acc64[k] + (double)acc[k]) * sc1 * sc2;
                 if (w.atomic_out) atomicAdd(row + Z0 + zl + k, v); else row[Z0 + zl + k] += v;
             }
     }
@@ -350,6 +378,7 @@ struct Layout3 {
     uint64_t *pmask;
     uint64_t *pairs_a, *pairs_b, *huge;
     uint32_t *tbeg, *tend, *seg_off, *seg_tmp;
+    int *wexp;
     void *sort_ws;
     size_t bytes;
 };
@@ -394,6 +423,7 @@ static Layout3 layout3(const ast_grid3d_params *p, void *ws)
     L.tend = c.take<uint32_t>(L.nbricks);
     L.seg_off = c.take<uint32_t>(L.nbricks + 1);
     L.seg_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(L.nbricks + 1));
+    L.wexp = c.take<int>(2);
     L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
     L.bytes = c.bytes();
     return L;
@@ -422,6 +452,7 @@ static P3 make_p3(const ast_grid3d_params *p, const double *pos, const double *h
     for (int c = 0; c < 3; ++c) a.box[c] = per ? p->box[c] : 0.0;
     a.small_max_vox = p->small_max_vox >= 0 ? p->small_max_vox : kDefaultSmallMaxVox;
     a.huge_min_bricks = p->huge_min_bricks >= 0 ? p->huge_min_bricks : kDefaultHugeMinBricks;
+    a.wexp = nullptr;
     return a;
 }
 
@@ -456,17 +487,25 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
     ast_project2d_stats st;
     memset(&st, 0, sizeof st);
     P3 a = make_p3(p, pos, h, prop, out);
-    a.pcount = L.pcount; a.pmask = L.pmask;
+    a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp;
     const size_t nvox = (size_t)p->nx * p->ny * p->nz;
     tm.begin(7);
     tk.begin(6);
     if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * nvox, s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));
+    AST_CUDA_TRY(cudaMemsetAsync(L.wexp, 0, 2 * sizeof(int), s));
     tk.end();
     uint64_t totals[2] = { 0, 0 };
     if (p->n > 0) {
         tk.begin(0);
+        {
+            int dev = 0, sm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+            const int64_t want = (p->n + 255) / 256;
+            wexp3_kernel<<<(unsigned)(want < (int64_t)sm * 8 ? want : (int64_t)sm * 8), 256, 0, s>>>(a, L.wexp);
+        }
         if (a.shape == SHAPE_CUBIC) bin3_kernel<SHAPE_CUBIC, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
         else if (a.shape == SHAPE_WENDLAND) bin3_kernel<SHAPE_WENDLAND, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
         else bin3_kernel<SHAPE_TABLE, true><<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.rec, L.block_pairs, L.block_huge);
@@ -475,23 +514,29 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_pairs, L.nb + 1, nullptr);
         scan_exclusive_kernel<uint64_t><<<1, kScanThreads, 0, s>>>(L.block_huge, L.nb + 1, nullptr);
         tk.end();
-        st.n_launches += 3;
+        st.n_launches += 4;
         AST_CUDA_TRY(cudaGetLastError());
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaStreamSynchronize(s));
     }
-    st.n_pairs = (int64_t)totals[0];
-    st.n_huge = (int64_t)totals[1];
-    if (totals[1] > (uint64_t)L.huge_cap || (totals[0] > 0 && p->pair_capacity <= 0)) {
-        set_error("capacity too small: need %llu huge entries (have %lld) and a positive pair_capacity",
-                  (unsigned long long)totals[1], (long long)L.huge_cap);
+    const uint64_t T = totals[0], H = totals[1];
+    st.n_pairs = (int64_t)T;
+    st.n_huge = (int64_t)H;
+    if (T + H > 0 && p->pair_capacity <= 0) {
+        set_error("pair_capacity is 0 but %llu pairs and %llu large-h particles need the brick path", (unsigned long long)T,
+                  (unsigned long long)H);
         if (stats) *stats = st;
         return AST_EWORKSPACE;
     }
-    if (totals[0] + totals[1] > 0) {
-        const uint64_t cap = (uint64_t)L.pair_cap;
-        const int64_t rounds = totals[0] ? (int64_t)((totals[0] + cap - 1) / cap) : 1;
+    if (T + H > 0) {
+        // pair_capacity and huge_capacity are WINDOWS: the pairs are walked through the pair window in rounds, the large-h list
+        // through its window likewise (every brick walks the entries of the current window), so no capacity can fail after the
+        // binning kernel has deposited the few-voxel particles
+        const uint64_t cap = (uint64_t)L.pair_cap, hcap = (uint64_t)L.huge_cap;
+        const uint64_t rounds = T ? (T + cap - 1) / cap : 0;
+        const uint64_t n_hwin = H ? (H + hcap - 1) / hcap : 0;
+        const uint64_t passes = rounds > n_hwin ? rounds : n_hwin;
         const int key_bits = ceil_log2_u64((uint64_t)L.nbricks) + a.img_shift;
         Acc3 c;
         c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
@@ -501,13 +546,16 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
         c.img_shift = a.img_shift;
         c.n_img = a.n_img;
         c.tab = a.tab;
+        c.wexp = L.wexp;
         for (int k = 0; k < 3; ++k) c.box[k] = a.box[k];
-        for (int64_t r = 0; r < rounds; ++r) {
-            const uint64_t w0 = (uint64_t)r * cap, w1 = (w0 + cap < totals[0]) ? w0 + cap : totals[0];
+        static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+        for (uint64_t r = 0; r < passes; ++r) {
+            // pass r: pair window r (if any left) together with large-h window r (if any left)
+            const uint64_t w0 = r < rounds ? r * cap : 0, w1 = r < rounds ? ((w0 + cap < T) ? w0 + cap : T) : 0;
+            const uint64_t h0 = r < n_hwin ? r * hcap : 0, h1 = r < n_hwin ? ((h0 + hcap < H) ? h0 + hcap : H) : 0;
             const int64_t nw = (int64_t)(w1 - w0);
             tk.begin(2);
-            emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, w0, w1, L.pairs_a, L.huge, r == 0,
-                                                                (uint64_t)L.huge_cap);
+            emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, w0, w1, L.pairs_a, L.huge, h0, h1);
             tk.end();
             int in_b = 0, nl = 0;
             tk.begin(3);
@@ -519,10 +567,8 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
             c.sorted = in_b ? L.pairs_b : L.pairs_a;
             if (nw > 0) brick_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
             tk.end();
-            c.n_huge = r == 0 ? (uint32_t)totals[1] : 0u;
+            c.n_huge = (uint32_t)(h1 - h0);
             // work items: long brick lists (cluster cores) are shared by several CTAs, see work_items.cuh
-            static int sm_count = 0;
-            if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
             const uint32_t seg_target = segment_target(nw, (int64_t)sm_count * 8);
             c.seg_off = L.seg_off; c.ntiles = (int)L.nbricks;
             tile_segments_kernel<<<(unsigned)((L.nbricks + 1 + 255) / 256), 256, 0, s>>>(L.tbeg, L.tend, c.n_huge, seg_target, (int)L.nbricks,
@@ -538,7 +584,7 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
             st.n_launches += 4 + nl + nls;
             AST_CUDA_TRY(cudaGetLastError());
         }
-        st.n_rounds = rounds;
+        st.n_rounds = (int64_t)passes;
     }
     tm.end();
     if (timing) {
@@ -588,8 +634,8 @@ extern "C" int ast_bin3d(const ast_grid3d_params *p, const double *pos, const do
         return AST_EWORKSPACE;
     }
     if (totals[0] + totals[1] > 0) {
-        emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, totals[0], L.pairs_a, L.huge, 1,
-                                                            (uint64_t)L.huge_cap);
+        emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, totals[0], L.pairs_a, L.huge, 0,
+                                                            totals[1]);
         AST_CUDA_TRY(cudaGetLastError());
         if (huge && totals[1]) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * totals[1], cudaMemcpyDeviceToDevice, s));
         if (pairs_sorted && totals[0]) {

@@ -53,6 +53,7 @@ static_assert(sizeof(Rec) == 32, "record is one 32-byte sector");
 // the call flush to zero), the tile sums are formed in those units and multiplied by 2^E_k in float64 when they are added to
 // the map.  Powers of two only: no rounding is added anywhere.
 constexpr int kZeroExp = -32768;
+constexpr int kExpBias = 1 << 20;       // stored maximum exponent = exponent + kExpBias > 0, so a zeroed control block means "none"
 __device__ __forceinline__ void split_weight(double c, float &m, int &e)
 {
     if (c == 0.0) { m = 0.f; e = kZeroExp; return; }
@@ -78,7 +79,9 @@ struct P2 {
     // written by K1 for the blocks that have pairs or large-h entries, read by K3 (which then enumerates tiles only once):
     uint32_t *pcount;                   // pairs of particle i
     uint32_t *pmask;                    // bit m: image m is tiled, bit 16 + m: image m is on the large-h list
-    int *wexp;                          // [AST_MAX_PROPS] maximum weight exponent of the call (atomicMax by K1), see split_weight
+    int *wexp;                          // [AST_MAX_PROPS] maximum weight exponent of the call + kExpBias (atomicMax by K1; 0 = no
+                                        // weight seen), see split_weight
+    unsigned long long *totals;         // [2] pairs and large-h entries of the call (atomicAdd by the K1 blocks that have any)
 };
 
 
@@ -223,7 +226,7 @@ __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0,
             r.e[k] = (int16_t)e;
             // running maximum of the call: a plain (possibly stale) read settles it for all but the first few warps, the
             // atomic only runs when this particle would raise it
-            if (k < NP && e != kZeroExp && e > __ldcg(p.wexp + k)) atomicMax(p.wexp + k, e);
+            if (k < NP && e != kZeroExp && e + kExpBias > __ldcg(p.wexp + k)) atomicMax(p.wexp + k, e + kExpBias);
         }
         rec[i] = r;
     }
@@ -255,6 +258,10 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(P2 p, Rec *__restrict_
     if (threadIdx.x == 0) {
         block_pairs[blk] = packed & ((1ull << 44) - 1ull);
         block_huge[blk] = packed >> 44;
+        if (packed != 0ull && p.totals) {
+            atomicAdd(p.totals, (unsigned long long)(packed & ((1ull << 44) - 1ull)));
+            if (packed >> 44) atomicAdd(p.totals + 1, (unsigned long long)(packed >> 44));
+        }
     }
 }
 
@@ -331,6 +338,7 @@ __global__ void __launch_bounds__(kBinThreads, MINB) bin_tma_kernel(P2 p, Rec *_
             if (blk + (int64_t)k * gridDim.x < n_full_blocks) issue(blk + (int64_t)k * gridDim.x, k);
     }
     uint32_t phase_bits = 0u;                                   // bit s = parity to wait for on stage s (kept in a register)
+    uint64_t cta_pairs = 0, cta_huge = 0;                       // thread 0: totals of the blocks this CTA handled
     int s = 0;
     for (; blk < n_full_blocks; blk += gridDim.x) {
         // the stage worked on in the previous iteration was released by the barrier at its end: refill it
@@ -356,8 +364,14 @@ __global__ void __launch_bounds__(kBinThreads, MINB) bin_tma_kernel(P2 p, Rec *_
         if (tid == 0) {
             block_pairs[blk] = packed & ((1ull << 44) - 1ull);
             block_huge[blk] = packed >> 44;
+            cta_pairs += packed & ((1ull << 44) - 1ull);
+            cta_huge += packed >> 44;
         }
         s = s + 1 == NSTAGE ? 0 : s + 1;
+    }
+    if (tid == 0) {                                   // one atomic per persistent CTA and count, none in the direct-deposit regime
+        if (cta_pairs) atomicAdd(p.totals, (unsigned long long)cta_pairs);
+        if (cta_huge) atomicAdd(p.totals + 1, (unsigned long long)cta_huge);
     }
 }
 
@@ -514,8 +528,8 @@ __global__ void __launch_bounds__(256) pair_record_kernel(Acc a, int64_t n, uint
     const float cscale = SHAPE == SHAPE_CUBIC ? 2.0f : 1.0f;
     pp[i] = make_float4(fx, fy, (float)a.dx * r.inv_h, (float)a.dy * r.inv_h);
     // weights relative to 2^E_k (E_k = largest exponent of the call): mantissa * 2^(e - E_k), at most 1 in magnitude
-    const float w0 = ldexpf(r.c[0], max((int)r.e[0] - a.wexp[0], -300));
-    const float w1 = NP > 1 ? ldexpf(r.c[1], max((int)r.e[1] - a.wexp[1], -300)) : 0.f;
+    const float w0 = ldexpf(r.c[0], max((int)r.e[0] - (a.wexp[0] - kExpBias), -300));
+    const float w1 = NP > 1 ? ldexpf(r.c[1], max((int)r.e[1] - (a.wexp[1] - kExpBias), -300)) : 0.f;
     pc[i] = make_float2(cscale * w0, cscale * w1);
 }
 
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
     double sc1[NP], sc2[NP];
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-        const int e = min(max(a.wexp[k], -2040), 2040), e1 = e / 2, e2 = e - e1;
+        const int e = min(max(a.wexp[k] - kExpBias, -2040), 2040), e1 = e / 2, e2 = e - e1;
         sc1[k] = __longlong_as_double((long long)(e1 + 1023) << 52);
         sc2[k] = __longlong_as_double((long long)(e2 + 1023) << 52);
     }
@@ -755,6 +769,7 @@ struct Layout2 {
     Rec *rec;
     uint64_t *pairs_a, *pairs_b, *huge, *hoff, *hoff_tmp;
     uint32_t *pcount, *pmask;
+    unsigned long long *ctrl;   // control block: totals[2], then the biased weight exponents (int[AST_MAX_PROPS]); zeroed per call
     int *wexp;
     RoundSet set;
     void *sort_ws;
@@ -795,7 +810,8 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.rec = c.take<Rec>(p->n > 0 ? p->n : 1);
     L.pcount = c.take<uint32_t>(p->n > 0 ? p->n : 1);
     L.pmask = c.take<uint32_t>(p->n > 0 ? p->n : 1);
-    L.wexp = c.take<int>(AST_MAX_PROPS);
+    L.ctrl = c.take<unsigned long long>(2 + (AST_MAX_PROPS * sizeof(int) + 7) / 8);
+    L.wexp = reinterpret_cast<int *>(L.ctrl ? L.ctrl + 2 : nullptr);
     L.pairs_a = c.take<uint64_t>(L.win);
     L.pairs_b = c.take<uint64_t>(L.win);
     L.huge = c.take<uint64_t>(L.huge_cap);
@@ -839,7 +855,7 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     a.small_max_px = p->small_max_px >= 0 ? p->small_max_px : kDefaultSmallMaxPx;
     a.huge_min_tiles = p->huge_min_tiles >= 0 ? p->huge_min_tiles : kDefaultHugeMinTiles;
     a.map_stride = (size_t)p->nx * (size_t)p->ny;
-    a.pcount = nullptr; a.pmask = nullptr; a.wexp = nullptr;
+    a.pcount = nullptr; a.pmask = nullptr; a.wexp = nullptr; a.totals = nullptr;
     return a;
 }
 
@@ -972,16 +988,13 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     ast_project2d_stats &st = R.st;
     R.a = make_p2(p, pos, h, prop, out);
     P2 &a = R.a;
-    a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp;
+    a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp; a.totals = L.ctrl;
     { int dev = 0; R.sm_count = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&R.sm_count, cudaDevAttrMultiProcessorCount, dev); }
 
     tm.begin(7);
     tk.begin(6);
     if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * a.map_stride * p->n_prop, s));
-    // entries 0..nb-1 are written by the binning kernels; only the sentinel entry nb (-> the totals after the scan) is zeroed
-    AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs + L.nb, 0, sizeof(uint64_t), s));
-    AST_CUDA_TRY(cudaMemsetAsync(L.block_huge + L.nb, 0, sizeof(uint64_t), s));
-    AST_CUDA_TRY(cudaMemsetAsync(L.wexp, 0x80, sizeof(int) * AST_MAX_PROPS, s));          // = -2139062144: below any exponent
+    AST_CUDA_TRY(cudaMemsetAsync(L.ctrl, 0, sizeof(unsigned long long) * 2 + sizeof(int) * AST_MAX_PROPS, s));     // totals, exponents
     tk.end();
     uint64_t totals[2] = { 0, 0 };
     if (p->n > 0) {
@@ -1041,13 +1054,21 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             }
         }
         tk.end();
-        tk.begin(1);
-        { int nl = 0; AST_CUDA_TRY(scan2_exclusive<uint64_t>(L.block_pairs, L.block_huge, L.nb + 1, L.scan_tmp, s, &nl)); st.n_launches += nl; }
-        tk.end();
         AST_CUDA_TRY(cudaGetLastError());
-        AST_CUDA_TRY(cudaMemcpyAsync(&totals[0], L.block_pairs + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        // the K1 blocks that have pairs or large-h entries added them to the control block: when nothing needs the tile path
+        // (the HBM-bound regime: every particle was deposited by K1) the call ends here, without the scan
+        AST_CUDA_TRY(cudaMemcpyAsync(totals, L.ctrl, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaStreamSynchronize(s));
+        if (totals[0] + totals[1] > 0) {
+            tk.begin(1);
+            // entries 0..nb-1 were written by the binning kernels; the sentinel entry nb becomes the total
+            AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs + L.nb, 0, sizeof(uint64_t), s));
+            AST_CUDA_TRY(cudaMemsetAsync(L.block_huge + L.nb, 0, sizeof(uint64_t), s));
+            int nl = 0;
+            AST_CUDA_TRY(scan2_exclusive<uint64_t>(L.block_pairs, L.block_huge, L.nb + 1, L.scan_tmp, s, &nl));
+            st.n_launches += nl;
+            tk.end();
+        }
     }
     const uint64_t T = totals[0], H = totals[1];
     st.n_pairs = (int64_t)T;
@@ -1134,7 +1155,7 @@ extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const
     }
     cudaStream_t s = (cudaStream_t)stream;
     P2 a = make_p2(p, pos, h, nullptr, nullptr);
-    a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp;
+    a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp; a.totals = nullptr;
     uint64_t *pa = L.pairs_a, *pb = L.pairs_b;
     const int64_t cap = L.win;
     uint64_t totals[2] = { 0, 0 };
