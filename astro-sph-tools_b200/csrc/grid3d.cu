@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kBin3Threads) bin3_kernel(P3 p, Rec3 *__restri
     }
 }
 
-__global__ void __launch_bounds__(kBin3Threads) emit3_kernel(P3 p, const uint64_t *__restrict__ pairs_excl,
+__global__ void __launch_bounds__(kBin3Threads, 3) emit3_kernel(P3 p, const uint64_t *__restrict__ pairs_excl,
                                                              const uint64_t *__restrict__ huge_excl, uint64_t w0, uint64_t w1,
                                                              uint64_t *__restrict__ pairs, uint64_t *__restrict__ huge,
                                                              uint64_t h0, uint64_t h1)

@@ -560,7 +560,10 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
     TileWork w;
     if (!resolve_work(a, w)) return;
     const int tile = w.tile;
-    const uint32_t beg = w.beg, total = w.cnt;
+    // the work item is the same for every thread of the CTA; saying so (broadcast from lane 0) lets the compiler keep the loop
+    // control in uniform registers and drop the divergence checks around the warp collectives below
+    const uint32_t beg = __shfl_sync(0xffffffffu, w.beg, 0), total = __shfl_sync(0xffffffffu, w.cnt, 0);
+    const uint32_t w_first = __shfl_sync(0xffffffffu, w.first, 0), w_step = __shfl_sync(0xffffffffu, w.step, 0);
     if (total == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tile / a.nty, ty = tile - tx * a.nty;
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
         for (int j = 0; j < NPIX; ++j) { acc[k][j] = 0.f; acc64[k][j] = 0.0; }
 
     int since_fold = 0;
-    for (uint32_t base = w.first; base < total; base += w.step) {
+    for (uint32_t base = w_first; base < total; base += w_step) {
         const uint32_t j = base + lane;
         bool hit = false, outer = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);

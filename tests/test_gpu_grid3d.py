@@ -119,3 +119,31 @@ def test_grid_against_the_literal_numpy_restatement():
     for kw in ({}, dict(small_max_vox=1 << 40), dict(small_max_vox=1, huge_min_bricks=1 << 40), dict(small_max_vox=1, huge_min_bricks=0)):
         g, _ = gpu_grid(pos, h, prop, size, lo, hi, **kw)
         assert rel_l2(g, ref) <= 1e-5 and abs(g.sum() - ref.sum()) <= 1e-6 * np.abs(ref).sum()
+
+
+def test_grid_capacities_are_windows_and_weights_keep_float64_range(oracle):
+    """(high) a large-h list longer than huge_capacity used to fail AFTER the binning kernel had deposited the
+    few-voxel particles -- and the retry added them twice in accumulate mode; (medium) float32 weights overflow / flush for
+    weights like 1e48 or 1e-59.  Both windows are walked in passes now; the brick path sums in units of 2^E."""
+    import torch
+    from astro_sph_tools_b200.tools.projections import Gridder3D
+    rng = np.random.default_rng(17)
+    n = 4000
+    pos = rng.uniform(0.0, 1.0, (n, 3))
+    h = rng.choice([0.004, 0.02, 0.05, 0.12], n, p=[0.4, 0.3, 0.2, 0.1])          # direct, bricks, large-h list
+    prop = rng.uniform(0.5, 1.5, n)
+    size, lo, hi = (48, 48, 48), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+    ref = oracle.grid3d(pos, h, prop, size, lo, hi)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    g = Gridder3D(pair_capacity=2000, huge_capacity=16, huge_min_bricks=8)
+    base = torch.full(size, 2.0, dtype=torch.float64, device="cuda")
+    out = g.grid(d(pos), d(h), d(prop), size, lo, hi, out=base, accumulate=True)
+    st = g.last_stats
+    assert st["n_huge"] > 16 and st["n_rounds"] > 4 and st["n_pairs"] > 2000
+    got = out.cpu().numpy() - 2.0
+    assert rel_l2(got, ref) <= 1e-5 and abs(got.sum() - ref.sum()) <= 1e-6 * np.abs(ref).sum()
+    for scale in (1e45, 1e-60, 1e300):
+        for kw in ({}, dict(small_max_vox=1, huge_min_bricks=1 << 40), dict(small_max_vox=1, huge_min_bricks=0)):
+            got, _ = gpu_grid(pos, h, prop * scale, size, lo, hi, **kw)
+            assert np.isfinite(got).all()
+            assert rel_l2(got / scale, ref) <= 1e-5 and abs((got / scale).sum() - ref.sum()) <= 1e-6 * np.abs(ref).sum()
