@@ -72,6 +72,7 @@ struct P2 {
     double norm_c;                      // norm(h) = norm_c / h^norm_dim
     ShapeTab tab;                       // AST_KERNEL_TABLE only
     Axis1 ax, ay;
+    double nxd1, nyd1;                  // (double)nx + 1, (double)ny + 1 (int -> double conversions cost XU cycles per particle)
     int ntx, nty, n_img, img_shift;     // sort key = tile_key << img_shift | image
     double box_a, box_b;                // periodic image m = 3*(ia+1) + (ib+1), shift = (ia*box_a, ib*box_b)
     int64_t small_max_px, huge_min_tiles;
@@ -128,10 +129,10 @@ __device__ __forceinline__ void deposit_small(const P2 &p, const Box2 &bb, doubl
 // the canonical bbox is at most 2x2 (class "direct" whenever small_max_px >= 4) and the four candidates are tested with
 // the exact float64 mask directly -- no bbox search.  This is the HBM-bound regime of the path.
 template <int SHAPE, int NP>
-__device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double pb, double R2, float inv_h2, const double *coef)
+__device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double pb, double R2, double inv_h2, const double *coef)
 {
     const double tx = AST_DMUL(AST_DSUB(pa, p.ax.vmin), p.ax.inv_d), ty = AST_DMUL(AST_DSUB(pb, p.ay.vmin), p.ay.inv_d);
-    if (!(tx > -2.0 && tx < (double)p.ax.n + 1.0 && ty > -2.0 && ty < (double)p.ay.n + 1.0)) return;   // also NaN / inf
+    if (!(tx > -2.0 && tx < p.nxd1 && ty > -2.0 && ty < p.nyd1)) return;   // also NaN / inf
     // floor() already is the sample index as a double: X(i) = vmin + i*d needs no int -> double conversion
     const double fx = floor(tx), fy = floor(ty);
     const int i0 = (int)fx, j0 = (int)fy;
@@ -145,50 +146,60 @@ __device__ __forceinline__ void deposit_subpixel(const P2 &p, double pa, double 
     }
     // exact float64 mask for the four candidates first, then ONE deposit loop over the hits of this lane: with four separate
     // predicated deposit blocks every block ran for the few lanes that hit that particular candidate (ncu: 22.8 of 32 lanes
-    // active over the kernel); here pass n serves the n-th hit of every lane that has one
-    float q2[4];
+    // active over the kernel); here pass n serves the n-th hit of every lane that has one.  Conversions run on the XU pipe
+    // (a quarter of the FP32 rate; ncu: XU 41 % busy in this kernel), so q^2 is narrowed to float32 per HIT, not per candidate.
+    double r2[4];
     unsigned hit = 0u;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const double r2 = AST_DADD(dx2[c >> 1], dy2[c & 1]);
-        q2[c] = (float)r2 * inv_h2;
-        hit |= (r2 < R2) ? (1u << c) : 0u;
+        r2[c] = AST_DADD(dx2[c >> 1], dy2[c & 1]);
+        hit |= (r2[c] < R2) ? (1u << c) : 0u;
     }
     while (hit) {
         const int c = __ffs((int)hit) - 1;
         hit &= hit - 1u;
-        const float s = (c & 2) ? ((c & 1) ? q2[3] : q2[2]) : ((c & 1) ? q2[1] : q2[0]);
-        const double f = (double)shape_eval<SHAPE>(fast_sqrt(s), p.tab);
+        const double rr = (c & 2) ? ((c & 1) ? r2[3] : r2[2]) : ((c & 1) ? r2[1] : r2[0]);
+        const double f = (double)shape_eval<SHAPE>(fast_sqrt((float)(rr * inv_h2)), p.tab);
         double *o = p.out + (size_t)(i0 + (c >> 1)) * (size_t)p.ay.n + (size_t)(j0 + (c & 1));
 #pragma unroll
         for (int k = 0; k < NP; ++k) atomicAdd(o + k * p.map_stride, coef[k] * f);
     }
 }
 
+// is the support of a particle below one pixel on both axes (sub-pixel fast path)?  One definition for K0 and K1.
+__device__ __forceinline__ bool is_subpixel(const P2 &p, double h2)
+{
+    return p.small_max_px >= 4 && h2 * p.ax.inv_d <= 1.0 - 1e-9 && h2 * p.ay.inv_d <= 1.0 - 1e-9;
+}
+
 // per-particle body of K1: classification, pair / large-h counts, direct deposit, record
-template <int SHAPE, bool DEPOSIT, int NP, bool PER>
+// SKIP_SUB: the sub-pixel particles of this block were already deposited by subpixel_tma_kernel (K0)
+template <int SHAPE, bool DEPOSIT, int NP, bool PER, bool SKIP_SUB = false>
 __device__ __forceinline__ void bin_particle(const P2 &p, int64_t i, double pa0, double pb0, double h, double *coef /* [NP] props */,
                                              Rec *__restrict__ rec, uint32_t &npairs, uint32_t &nhuge, uint32_t &mask)
 {
     const double R2 = radius2(h);
     const double h2 = AST_DMUL(2.0, h);
     if (!(h > 0.0 && h2 < INFINITY)) return;
+    const bool subpixel = is_subpixel(p, h2);
+    if (SKIP_SUB && subpixel) return;
     float inv_h2 = 0.f, inv_hf = 0.f;
+    double inv_h2d = 0.0;
     if (DEPOSIT) {
         const double inv_h = fast_rcp64(h);
         const double nrm = norm_from_inv_h(p, inv_h);
 #pragma unroll
         for (int k = 0; k < NP; ++k) coef[k] *= nrm;
         inv_hf = (float)inv_h;
-        inv_h2 = (float)(inv_h * inv_h);
+        inv_h2d = inv_h * inv_h;
+        inv_h2 = (float)inv_h2d;
     }
     const int n_img = PER ? p.n_img : 1;                       // compile-time 1 without periodic images
-    const bool subpixel = p.small_max_px >= 4 && h2 * p.ax.inv_d <= 1.0 - 1e-9 && h2 * p.ay.inv_d <= 1.0 - 1e-9;
     if (subpixel) {
         if (DEPOSIT)
             for (int m = 0; m < n_img; ++m)
                 deposit_subpixel<SHAPE, NP>(p, AST_DADD(pa0, image_shift_a(n_img, p.box_a, m)),
-                                            AST_DADD(pb0, image_shift_b(n_img, p.box_b, m)), R2, inv_h2, coef);
+                                            AST_DADD(pb0, image_shift_b(n_img, p.box_b, m)), R2, inv_h2d, coef);
         return;
     }
     bool need_rec = false;
@@ -305,25 +316,34 @@ struct __align__(128) BinStage {
     double prop[NP][kBinThreads];
 };
 
-// NSTAGE stages of 256 particles per CTA: NSTAGE - 1 bulk copies are in flight while one stage is worked on (a B200 needs
-// ~35 KB in flight per SM to cover HBM latency at full bandwidth; two stages of 10 KB on three resident CTAs were just short).
-template <int SHAPE, int NP, bool PER, int NSTAGE, int MINB>
-__global__ void __launch_bounds__(kBinThreads, MINB) bin_tma_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
-                                                                    uint64_t *__restrict__ block_huge, int64_t n_full_blocks)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K0 (round 2): the sub-pixel pass.  Same persistent TMA pipeline as K1, but the only thing it does is the sub-pixel fast path:
+// a particle whose support is below one pixel is deposited here (exact float64 mask on its 2x2 candidates), anything else only
+// marks its block as "heavy" for K1.  The point is occupancy: this path needs 40 registers, the general classification
+// 64-80, and the HBM-bound regime of the whole library (every particle sub-pixel) is latency-limited -- ncu on K1 there:
+// issue 72 %, 2.0 eligible warps per scheduler, "wait" 2.1 and barrier 1.3 stalls per issue at 4 CTAs per SM.  With SPH-realistic
+// supports K0 streams the inputs once for nothing: 0.9 ms of a 278 ms step at config 3.
+template <int SHAPE, int NP, bool PER>
+__global__ void __launch_bounds__(kBinThreads, 6) subpixel_tma_kernel(P2 p, uint64_t *__restrict__ block_pairs,
+                                                                      uint64_t *__restrict__ block_huge, uint8_t *__restrict__ block_heavy,
+                                                                      unsigned long long *__restrict__ heavy_count, int64_t n_full_blocks)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BinStage<NP> *st = reinterpret_cast<BinStage<NP> *>(smem_raw);
-    __shared__ __align__(8) uint64_t bar[NSTAGE];
-    __shared__ uint64_t red[34];
+    __shared__ __align__(8) uint64_t bar[2];
     const int tid = threadIdx.x;
     constexpr uint32_t kBytes = (uint32_t)sizeof(BinStage<NP>);
     if (tid == 0) {
-#pragma unroll
-        for (int k = 0; k < NSTAGE; ++k) mbar_init(&bar[k], 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int64_t blk, int s) {          // one elected thread: arm the barrier, launch the bulk copies
+    auto issue = [&](int64_t blk, int s) {
         mbar_expect_tx(&bar[s], kBytes);
         const int64_t i0 = blk * kBinThreads;
         tma_load_1d(st[s].pos, p.pos + 3 * i0, 3 * kBinThreads * 8, &bar[s]);
@@ -332,27 +352,102 @@ __global__ void __launch_bounds__(kBinThreads, MINB) bin_tma_kernel(P2 p, Rec *_
         for (int k = 0; k < NP; ++k) tma_load_1d(st[s].prop[k], p.prop[k] + i0, kBinThreads * 8, &bar[s]);
     };
     int64_t blk = blockIdx.x;
+    if (tid == 0 && blk < n_full_blocks) issue(blk, 0);
+    uint32_t phase_bits = 0u;
+    unsigned cta_heavy = 0u;
+    const int n_img = PER ? p.n_img : 1;
+    for (int it = 0; blk < n_full_blocks; blk += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int64_t next = blk + gridDim.x;
+        if (tid == 0 && next < n_full_blocks) issue(next, s ^ 1);     // stage s^1 was released by the barrier below
+        mbar_wait(&bar[s], (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
+        const double pa0 = st[s].pos[3 * tid + p.a_col], pb0 = st[s].pos[3 * tid + p.b_col], h = st[s].h[tid];
+        double coef[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) coef[k] = st[s].prop[k][tid];
+        const double h2 = AST_DMUL(2.0, h);
+        bool heavy = false;
+        if (h > 0.0 && h2 < INFINITY) {
+            if (is_subpixel(p, h2)) {
+                const double inv_h = fast_rcp64(h), nrm = norm_from_inv_h(p, inv_h), R2 = radius2(h);
+#pragma unroll
+                for (int k = 0; k < NP; ++k) coef[k] *= nrm;
+                for (int m = 0; m < n_img; ++m)
+                    deposit_subpixel<SHAPE, NP>(p, AST_DADD(pa0, image_shift_a(n_img, p.box_a, m)),
+                                                AST_DADD(pb0, image_shift_b(n_img, p.box_b, m)), R2, inv_h * inv_h, coef);
+            } else {
+                heavy = true;
+            }
+        }
+        const int any_heavy = __syncthreads_or(heavy);            // also releases stage s for the next bulk copy
+        if (tid == 0) {
+            block_heavy[blk] = any_heavy ? 1 : 0;
+            if (any_heavy) ++cta_heavy;
+            else { block_pairs[blk] = 0; block_huge[blk] = 0; }  // K1 skips the block: its scan entries are zero
+        }
+    }
+    if (tid == 0 && cta_heavy) atomicAdd(heavy_count, (unsigned long long)cta_heavy);
+}
+
+// NSTAGE stages of 256 particles per CTA: NSTAGE - 1 bulk copies are in flight while one stage is worked on.  With K0 in
+// front (SKIP_SUB) the CTA only visits the blocks K0 marked heavy: thread 0 looks up the next marked block of its stride and
+// publishes its index with the stage (or -1 at the end, arriving on the barrier itself).
+template <int SHAPE, int NP, bool PER, int NSTAGE, int MINB, bool SKIP_SUB>
+__global__ void __launch_bounds__(kBinThreads, MINB) bin_tma_kernel(P2 p, Rec *__restrict__ rec, uint64_t *__restrict__ block_pairs,
+                                                                    uint64_t *__restrict__ block_huge, int64_t n_full_blocks,
+                                                                    const uint8_t *__restrict__ block_heavy,
+                                                                    const unsigned long long *__restrict__ heavy_count)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BinStage<NP> *st = reinterpret_cast<BinStage<NP> *>(smem_raw);
+    __shared__ __align__(8) uint64_t bar[NSTAGE];
+    __shared__ int64_t sblk[NSTAGE];
+    __shared__ uint64_t red[34];
+    if (SKIP_SUB && *heavy_count == 0ull) return;                   // nothing for K1: every particle was sub-pixel (or invalid)
+    const int tid = threadIdx.x;
+    constexpr uint32_t kBytes = (uint32_t)sizeof(BinStage<NP>);
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < NSTAGE - 1; ++k)
-            if (blk + (int64_t)k * gridDim.x < n_full_blocks) issue(blk + (int64_t)k * gridDim.x, k);
+        for (int k = 0; k < NSTAGE; ++k) mbar_init(&bar[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int64_t scan = blockIdx.x;                                     // thread 0: next candidate block of this CTA's stride
+    auto fill = [&](int s) {          // one elected thread: next block to visit -> stage s (bulk copies), or the end marker
+        while (SKIP_SUB && scan < n_full_blocks && !block_heavy[scan]) scan += gridDim.x;
+        const int64_t blk = scan < n_full_blocks ? scan : -1;
+        scan += gridDim.x;
+        sblk[s] = blk;
+        if (blk < 0) { mbar_arrive(&bar[s]); return; }
+        mbar_expect_tx(&bar[s], kBytes);
+        const int64_t i0 = blk * kBinThreads;
+        tma_load_1d(st[s].pos, p.pos + 3 * i0, 3 * kBinThreads * 8, &bar[s]);
+        tma_load_1d(st[s].h, p.h + i0, kBinThreads * 8, &bar[s]);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) tma_load_1d(st[s].prop[k], p.prop[k] + i0, kBinThreads * 8, &bar[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NSTAGE - 1; ++k) fill(k);
     }
     uint32_t phase_bits = 0u;                                   // bit s = parity to wait for on stage s (kept in a register)
     uint64_t cta_pairs = 0, cta_huge = 0;                       // thread 0: totals of the blocks this CTA handled
     int s = 0;
-    for (; blk < n_full_blocks; blk += gridDim.x) {
+    for (;;) {
         // the stage worked on in the previous iteration was released by the barrier at its end: refill it
-        const int64_t ahead = blk + (int64_t)(NSTAGE - 1) * gridDim.x;
-        if (tid == 0 && ahead < n_full_blocks) issue(ahead, s == 0 ? NSTAGE - 1 : s - 1);
+        if (tid == 0) fill(s == 0 ? NSTAGE - 1 : s - 1);
         mbar_wait(&bar[s], (phase_bits >> s) & 1u);
         phase_bits ^= 1u << s;
+        const int64_t blk = sblk[s];
+        if (blk < 0) break;                                     // uniform: no block left for this CTA
         const int64_t i = blk * kBinThreads + tid;
         const double pa0 = st[s].pos[3 * tid + p.a_col], pb0 = st[s].pos[3 * tid + p.b_col], h = st[s].h[tid];
         double coef[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) coef[k] = st[s].prop[k][tid];
         uint32_t npairs = 0, nhuge = 0, mask = 0;
-        bin_particle<SHAPE, true, NP, PER>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge, mask);
+        bin_particle<SHAPE, true, NP, PER, SKIP_SUB>(p, i, pa0, pb0, h, coef, rec, npairs, nhuge, mask);
         // one barrier-with-vote tells whether any thread has pairs / large-h entries at all (in the direct-deposit regime none
         // has): only then pay for the full block reduction.  The barrier also releases stage s for the next bulk copy.
         uint64_t packed = ((uint64_t)nhuge << 44) | (uint64_t)npairs;
@@ -772,8 +867,10 @@ struct Layout2 {
     Rec *rec;
     uint64_t *pairs_a, *pairs_b, *huge, *hoff, *hoff_tmp;
     uint32_t *pcount, *pmask;
-    unsigned long long *ctrl;   // control block: totals[2], then the biased weight exponents (int[AST_MAX_PROPS]); zeroed per call
+    unsigned long long *ctrl;   // control block: totals[2], heavy block count, then the biased weight exponents (int[AST_MAX_PROPS]);
+                                // zeroed per call
     int *wexp;
+    uint8_t *block_heavy;       // nb flags written by K0: the block holds particles K1 has to classify
     RoundSet set;
     void *sort_ws;
     size_t bytes;
@@ -813,8 +910,9 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.rec = c.take<Rec>(p->n > 0 ? p->n : 1);
     L.pcount = c.take<uint32_t>(p->n > 0 ? p->n : 1);
     L.pmask = c.take<uint32_t>(p->n > 0 ? p->n : 1);
-    L.ctrl = c.take<unsigned long long>(2 + (AST_MAX_PROPS * sizeof(int) + 7) / 8);
-    L.wexp = reinterpret_cast<int *>(L.ctrl ? L.ctrl + 2 : nullptr);
+    L.ctrl = c.take<unsigned long long>(3 + (AST_MAX_PROPS * sizeof(int) + 7) / 8);
+    L.wexp = reinterpret_cast<int *>(L.ctrl ? L.ctrl + 3 : nullptr);
+    L.block_heavy = c.take<uint8_t>(L.nb + 1);
     L.pairs_a = c.take<uint64_t>(L.win);
     L.pairs_b = c.take<uint64_t>(L.win);
     L.huge = c.take<uint64_t>(L.huge_cap);
@@ -848,6 +946,7 @@ static P2 make_p2(const ast_project2d_params *p, const double *pos, const double
     a.tab.scale = 0.5f * (float)p->kernel_table_n;
     a.ax = make_axis(p->x_min, p->x_max, p->nx);
     a.ay = make_axis(p->y_min, p->y_max, p->ny);
+    a.nxd1 = (double)p->nx + 1.0; a.nyd1 = (double)p->ny + 1.0;
     a.ntx = (p->nx + TILE - 1) / TILE;
     a.nty = (p->ny + TILE - 1) / TILE;
     const bool per = (p->flags & AST_FLAG_PERIODIC) != 0;
@@ -997,7 +1096,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     tm.begin(7);
     tk.begin(6);
     if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * a.map_stride * p->n_prop, s));
-    AST_CUDA_TRY(cudaMemsetAsync(L.ctrl, 0, sizeof(unsigned long long) * 2 + sizeof(int) * AST_MAX_PROPS, s));     // totals, exponents
+    AST_CUDA_TRY(cudaMemsetAsync(L.ctrl, 0, sizeof(unsigned long long) * 3 + sizeof(int) * AST_MAX_PROPS, s));     // totals, heavy count, exponents
     tk.end();
     uint64_t totals[2] = { 0, 0 };
     if (p->n > 0) {
@@ -1011,22 +1110,38 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
             const int64_t n_full = (aligned && use_tma) ? p->n / kBinThreads : 0;
             if (n_full > 0) {
                 // persistent grid: one wave of resident CTAs (multiple of the SM count)
-#define AST_LAUNCH_TMA2(SH, NPV, PERV, NST, MB)                                                                            \
+                // K0 (sub-pixel pass, 40 registers, 6 CTAs per SM) deposits every particle whose support is below one pixel and
+                // marks the other blocks; K1 (general classification, 80 registers) then visits the marked blocks only and
+                // returns at once when there is none.  AST_BIN_K0=0 runs K1 alone over all blocks.
+                static const bool use_k0 = env_flag("AST_BIN_K0", true);
+#define AST_LAUNCH_K(KERN, SMEM, ...)                                                                                   \
     do {                                                                                                                \
-        auto kern = bin_tma_kernel<SH, NPV, PERV, NST, MB>;                                                             \
-        const size_t smem = (size_t)NST * sizeof(BinStage<NPV>);                                                        \
+        auto kern = KERN;                                                                                               \
+        const size_t smem = (SMEM);                                                                                     \
         if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         int per_sm = 1;                                                                                                 \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBinThreads, smem);                                \
-        int64_t grid = (int64_t)R.sm_count * (per_sm > 0 ? per_sm : 1);                                                 \
+        int64_t grid = (int64_t)R.sm_count * (per_sm > 0 ? per_sm : 1);     /* persistent: one wave of resident CTAs */  \
         if (grid > n_full) grid = n_full;                                                                               \
-        kern<<<(unsigned)grid, kBinThreads, smem, s>>>(a, L.rec, L.block_pairs, L.block_huge, n_full);                  \
+        kern<<<(unsigned)grid, kBinThreads, smem, s>>>(__VA_ARGS__);                                                    \
     } while (0)
-    // measured (benchmarks/bin_probe.py, 512^3 particles with sub-pixel supports; stages x CTAs per SM): 2 x 3 (80 registers)
-    // 1.581 ms, 4 x 3: 1.587, 2 x 4 (64 registers, no spills): 1.469, 4 x 4: 1.488, 2 x 5 (48 registers, spills): 1.608,
-    // 2 x 6: 2.000 -- occupancy, not pipeline depth, is what hides the latency here.  (With SPH-realistic supports the
-    // 64-register build costs 0.5 ms of a 284 ms step: 7.69 instead of 7.18 ms.)
-#define AST_LAUNCH_TMA(SH, NPV, PERV) AST_LAUNCH_TMA2(SH, NPV, PERV, 2, 4)
+    // measured on K1 alone (benchmarks/bin_probe.py, 512^3 particles with sub-pixel supports; stages x CTAs per SM): 2 x 3
+    // (80 registers) 1.581 ms, 4 x 3: 1.587, 2 x 4 (64 registers, no spills): 1.469, 4 x 4: 1.488, 2 x 5 (48 registers,
+    // spills): 1.608, 2 x 6: 2.000 -- occupancy, not pipeline depth, hides the latency; hence K0.  With SPH-realistic supports
+    // the 80-register build of K1 is the faster one (7.18 against 7.69 ms at config 3).
+#define AST_LAUNCH_TMA(SH, NPV, PERV)                                                                                   \
+    do {                                                                                                                \
+        if (use_k0) {                                                                                                   \
+            AST_LAUNCH_K((subpixel_tma_kernel<SH, NPV, PERV>), 2 * sizeof(BinStage<NPV>), a, L.block_pairs, L.block_huge, \
+                         L.block_heavy, L.ctrl + 2, n_full);                                                            \
+            AST_LAUNCH_K((bin_tma_kernel<SH, NPV, PERV, 2, 3, true>), 2 * sizeof(BinStage<NPV>), a, L.rec, L.block_pairs, \
+                         L.block_huge, n_full, L.block_heavy, L.ctrl + 2);                                              \
+            st.n_launches += 1;                                                                                         \
+        } else {                                                                                                        \
+            AST_LAUNCH_K((bin_tma_kernel<SH, NPV, PERV, 2, 4, false>), 2 * sizeof(BinStage<NPV>), a, L.rec, L.block_pairs, \
+                         L.block_huge, n_full, nullptr, nullptr);                                                       \
+        }                                                                                                               \
+    } while (0)
                 {
                     const bool per = a.n_img > 1;
 #define AST_D2(SH) do { if (p->n_prop == 1) { if (per) AST_LAUNCH_TMA(SH, 1, true); else AST_LAUNCH_TMA(SH, 1, false); } \
@@ -1037,7 +1152,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
 #undef AST_D2
                 }
 #undef AST_LAUNCH_TMA
-#undef AST_LAUNCH_TMA2
+#undef AST_LAUNCH_K
                 st.n_launches += 1;
             }
             const int64_t n_rest = L.nb - n_full;

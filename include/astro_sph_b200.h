@@ -77,9 +77,10 @@ typedef struct ast_project2d_params {
     double x_min, x_max, y_min, y_max;
     double box_a, box_b;         /* periodic lengths along the two in-plane axes (AST_FLAG_PERIODIC) */
     int64_t small_max_px;        /* bbox area (pixels) up to which a particle is deposited directly; <0 = default */
-    int64_t huge_min_tiles;      /* tile-bbox count above which a particle goes to the global list; <0 = default */
-    int64_t pair_capacity;       /* (tile, particle) pairs the workspace holds per round */
-    int64_t huge_capacity;       /* entries of the global large-h list */
+    int64_t huge_min_tiles;      /* tile-bbox count above which a particle image goes on the large-h list and is split across its
+                                    tiles by a warp of its own (huge_tiles_kernel); <0 = default */
+    int64_t pair_capacity;       /* WINDOW of (tile, particle) pairs the workspace holds; more pairs take more rounds */
+    int64_t huge_capacity;       /* WINDOW of large-h list entries; a longer list is walked window by window */
     const float *kernel_table;   /* AST_KERNEL_TABLE: DEVICE array of 2*kernel_table_n floats, entry j = {f(q_j), f(q_j+1)-f(q_j)},
                                     q_j = 2j/kernel_table_n; linear interpolation, 0 for q >= 2 */
     int32_t kernel_table_n;      /* number of intervals */
@@ -87,9 +88,9 @@ typedef struct ast_project2d_params {
 } ast_project2d_params;
 
 typedef struct ast_project2d_stats {
-    int64_t n_pairs;             /* (tile, particle-image) pairs emitted */
-    int64_t n_huge;              /* particle-images in the global large-h list */
-    int64_t n_rounds;            /* passes over the pair window (1 unless pair_capacity < n_pairs) */
+    int64_t n_pairs;             /* (tile, particle-image) pairs emitted, those of the large-h list included */
+    int64_t n_huge;              /* particle-images on the large-h list */
+    int64_t n_rounds;            /* passes over the pair window (1 unless pair_capacity < n_pairs or huge_capacity < n_huge) */
     int64_t n_launches;          /* kernels launched by this call */
     float stage_ms[8];           /* AST_FLAG_TIMING: 0 bin+direct deposit, 1 scan, 2 emit, 3 sort, 4 tile ranges,
                                     5 tile accumulate, 6 memset, 7 total */
@@ -97,8 +98,13 @@ typedef struct ast_project2d_stats {
 
 int ast_project2d_workspace_bytes(const ast_project2d_params *p, size_t *bytes /* host */);
 
-/* prop: HOST array of n_prop DEVICE pointers.  out: n_prop*nx*ny doubles.  Synchronises the stream once
- * (to read the pair count) unless every particle is deposited directly.  stats: host, nullable. */
+/* prop: HOST array of n_prop DEVICE pointers.  out: n_prop*nx*ny doubles.  stats: host, nullable.
+ * Synchronises the stream once after the binning kernel (a 16-byte read of the pair / large-h totals; when both are zero
+ * the call ends there) and once more per large-h window.  pair_capacity and huge_capacity are windows: no value > 0 can
+ * make the call fail, and nothing is deposited twice.  The one AST_EWORKSPACE that can be returned AFTER `out` has been
+ * written to (the direct deposits of the binning kernel) is pair_capacity <= 0 with particles that need the tile path.
+ * Weights are float64 and keep float64 range (the tile path stores mantissa + exponent, sums in units of the call's largest
+ * power of two, scales back in float64). */
 int ast_project2d(const ast_project2d_params *p, const double *pos, const double *h,
                   const double *const *prop, double *out, void *workspace, size_t workspace_bytes,
                   void *stream, ast_project2d_stats *stats);
@@ -108,8 +114,11 @@ int ast_project2d(const ast_project2d_params *p, const double *pos, const double
  * bbox: n_img*N*4 int32 (x0,x1,y0,y1 inclusive; empty = 0,-1,0,-1), row j = m*N + i.
  * cls:  n_img*N uint8 (0 empty, 1 direct, 2 tiled, 3 global list).
  * pairs_emit / pairs_sorted: pair_capacity uint64 each, element = (sort_key << 32) | particle,
- *   sort_key = tile_key * (periodic ? 16 : 1) + image.  huge: huge_capacity uint64 = (image << 32) | particle.
- * counts (host): [0] pairs, [1] huge.  Any output pointer may be null.  Synchronises. */
+ *   sort_key = tile_key * (periodic ? 16 : 1) + image; the tiled pairs in emit order (particle, image, tx, ty ascending)
+ *   are followed by the pairs of the large-h entries (entry by entry in list order, tiles tx-then-ty ascending).
+ *   huge: huge_capacity uint64 = (image << 32) | particle.
+ * counts (host): [0] pairs (large-h pairs included), [1] large-h entries.  Any output pointer may be null.  Synchronises.
+ * Here the capacities ARE limits (AST_EWORKSPACE when the caller's arrays are too small); no map is touched. */
 int ast_bin2d(const ast_project2d_params *p, const double *pos, const double *h,
               int32_t *bbox, uint8_t *cls, uint64_t *pairs_emit, uint64_t *pairs_sorted, uint64_t *huge,
               int64_t *counts, void *workspace, size_t workspace_bytes, void *stream);
