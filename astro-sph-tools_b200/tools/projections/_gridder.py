@@ -84,16 +84,11 @@ class Gridder3D:
             out = torch.empty((p.nx, p.ny, p.nz), dtype=torch.float64, device=self.device)
         stats = _lib.Project2DStats()
         with torch.cuda.device(self.device), self._lock:
-            while True:
-                ws = self.workspace(p)
-                rc = self.lib.ast_grid3d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), _lib.ptr(prop), _lib.ptr(out), _lib.ptr(ws),
-                                         C.c_size_t(ws.numel()), _lib.stream_ptr(stream), C.byref(stats))
-                if rc == _lib.AST_EWORKSPACE and stats.n_huge > p.huge_capacity:
-                    self.huge_capacity = int(stats.n_huge * 1.25) + 1024
-                    p.huge_capacity = self.huge_capacity
-                    continue
-                _lib.check(rc)
-                break
+            # pair_capacity / huge_capacity are windows (the library walks any number of pairs and large-h entries through them
+            # in passes): no capacity can fail once the direct deposits have started, nothing is retried
+            ws = self.workspace(p)
+            _lib.check(self.lib.ast_grid3d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), _lib.ptr(prop), _lib.ptr(out), _lib.ptr(ws),
+                                           C.c_size_t(ws.numel()), _lib.stream_ptr(stream), C.byref(stats)))
         self.last_stats = dict(n_pairs=stats.n_pairs, n_huge=stats.n_huge, n_rounds=stats.n_rounds,
                                n_launches=stats.n_launches, stage_ms=list(stats.stage_ms))
         return out
