@@ -537,7 +537,7 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
         const uint64_t rounds = T ? (T + cap - 1) / cap : 0;
         const uint64_t n_hwin = H ? (H + hcap - 1) / hcap : 0;
         const uint64_t passes = rounds > n_hwin ? rounds : n_hwin;
-        const int key_bits = ceil_log2_u64((uint64_t)L.nbricks) + a.img_shift;
+        const int key_bits = ceil_log2_u64((uint64_t)L.nbricks);     // the image bits below the brick key are NOT sorted on
         Acc3 c;
         c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
         for (int k = 0; k < 3; ++k) {
@@ -559,7 +559,7 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
             tk.end();
             int in_b = 0, nl = 0;
             tk.begin(3);
-            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32, key_bits, L.sort_ws, s, &in_b, &nl));
+            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32 + a.img_shift, key_bits, L.sort_ws, s, &in_b, &nl));
             tk.end();
             tk.begin(4);
             AST_CUDA_TRY(cudaMemsetAsync(L.tbeg, 0, sizeof(uint32_t) * L.nbricks, s));
@@ -640,8 +640,8 @@ extern "C" int ast_bin3d(const ast_grid3d_params *p, const double *pos, const do
         if (huge && totals[1]) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * totals[1], cudaMemcpyDeviceToDevice, s));
         if (pairs_sorted && totals[0]) {
             int in_b = 0;
-            const int key_bits = ceil_log2_u64((uint64_t)L.nbricks) + a.img_shift;
-            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, (int64_t)totals[0], 32, key_bits, L.sort_ws, s, &in_b));
+            const int key_bits = ceil_log2_u64((uint64_t)L.nbricks);
+            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, (int64_t)totals[0], 32 + a.img_shift, key_bits, L.sort_ws, s, &in_b));
             AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? L.pairs_b : L.pairs_a, sizeof(uint64_t) * totals[0],
                                          cudaMemcpyDeviceToDevice, s));
         }

@@ -1016,9 +1016,9 @@ static int prep_round(Run2 &R, uint64_t w0, uint64_t w1, uint64_t T, uint64_t ba
     }
     R.tk->end();
     int in_b = 0, nl = 0;
-    const int key_bits = ceil_log2_u64((uint64_t)L.ntiles) + R.a.img_shift;
+    const int key_bits = ceil_log2_u64((uint64_t)L.ntiles);     // the image bits below the tile key are NOT sorted on
     R.tk->begin(3);
-    AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32, key_bits, L.sort_ws, q, &in_b, &nl));
+    AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32 + R.a.img_shift, key_bits, L.sort_ws, q, &in_b, &nl));
     R.tk->end();
     R.st.n_launches += nl;
     R.tk->begin(4);
@@ -1320,8 +1320,8 @@ extern "C" int ast_bin2d(const ast_project2d_params *p, const double *pos, const
         if (huge && H) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, s));
         if (pairs_sorted && total) {
             int in_b = 0;
-            const int key_bits = ceil_log2_u64((uint64_t)L.ntiles) + a.img_shift;
-            AST_CUDA_TRY(radix_sort_u64(pa, pb, (int64_t)total, 32, key_bits, L.sort_ws, s, &in_b));
+            const int key_bits = ceil_log2_u64((uint64_t)L.ntiles);
+            AST_CUDA_TRY(radix_sort_u64(pa, pb, (int64_t)total, 32 + a.img_shift, key_bits, L.sort_ws, s, &in_b));
             AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? pb : pa, sizeof(uint64_t) * total, cudaMemcpyDeviceToDevice, s));
         }
     }

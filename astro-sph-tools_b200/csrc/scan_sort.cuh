@@ -292,10 +292,12 @@ inline cudaError_t scan2_exclusive(T *a, T *b, int64_t n, T *tmp, cudaStream_t s
 constexpr int kSortWarps = 8;
 constexpr int kSortWarpItems = 1024;
 constexpr int kSortBlockItems = kSortWarps * kSortWarpItems;   // 8192
-constexpr int kRadix = 256;
+constexpr int kSortThreads = kSortWarps * 32;                  // 256
+constexpr int kRadixMaxBits = 9;                               // digits of up to 9 bits (512 buckets): 18 key bits = 2 passes
+constexpr int kRadixMax = 1 << kRadixMaxBits;
 
 inline int64_t sort_num_blocks(int64_t n) { return (n + kSortBlockItems - 1) / kSortBlockItems; }
-inline size_t sort_table_entries(int64_t n) { return (size_t)sort_num_blocks(n > 0 ? n : 1) * kRadix; }
+inline size_t sort_table_entries(int64_t n) { return (size_t)sort_num_blocks(n > 0 ? n : 1) * kRadixMax; }
 inline size_t sort_workspace_bytes(int64_t n)
 {
     size_t t = (sort_table_entries(n) + 64) * sizeof(uint32_t);
@@ -303,18 +305,21 @@ inline size_t sort_workspace_bytes(int64_t n)
     return t + scan_workspace_bytes<uint32_t>((int64_t)sort_table_entries(n));
 }
 
-static __global__ void __launch_bounds__(kSortWarps * 32)
+// RADIX = number of buckets of this pass (256 or 512); thread t owns buckets t, t + 256, ...
+template <int RADIX>
+static __global__ void __launch_bounds__(kSortThreads)
 sort_hist_kernel(const uint64_t *__restrict__ in, int64_t n, int shift, uint32_t mask, uint32_t *__restrict__ table,
                  int64_t nblocks)
 {
-    __shared__ uint32_t hist[kRadix];
+    __shared__ uint32_t hist[RADIX];
     const int tid = threadIdx.x;
-    hist[tid] = 0;
+#pragma unroll
+    for (int d = tid; d < RADIX; d += kSortThreads) hist[d] = 0;
     __syncthreads();
     const int64_t b = blockIdx.x;
     const int64_t beg = b * kSortBlockItems;
     const int64_t end = beg + kSortBlockItems < n ? beg + kSortBlockItems : n;
-    for (int64_t i0 = beg; i0 < end; i0 += kSortWarps * 32) {     // uniform trip count for the whole block
+    for (int64_t i0 = beg; i0 < end; i0 += kSortThreads) {     // uniform trip count for the whole block
         int64_t i = i0 + tid;
         uint32_t d = i < end ? ((uint32_t)(in[i] >> shift) & mask) : 0xffffffffu;
         // aggregate equal digits inside the warp before touching shared memory
@@ -322,16 +327,18 @@ sort_hist_kernel(const uint64_t *__restrict__ in, int64_t n, int shift, uint32_t
         if (d != 0xffffffffu && (int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
     }
     __syncthreads();
-    table[(int64_t)tid * nblocks + b] = hist[tid];
+#pragma unroll
+    for (int d = tid; d < RADIX; d += kSortThreads) table[(int64_t)d * nblocks + b] = hist[d];
 }
 
-static __global__ void __launch_bounds__(kSortWarps * 32)
+template <int RADIX>
+static __global__ void __launch_bounds__(kSortThreads)
 sort_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int64_t n, int shift, uint32_t mask,
                     const uint32_t *__restrict__ table, int64_t nblocks)
 {
-    __shared__ uint32_t wbase[kSortWarps][kRadix];
+    __shared__ uint32_t wbase[kSortWarps][RADIX];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kSortWarps * kRadix; i += kSortWarps * 32) (&wbase[0][0])[i] = 0;
+    for (int i = tid; i < kSortWarps * RADIX; i += kSortThreads) (&wbase[0][0])[i] = 0;
     __syncthreads();
     const int64_t b = blockIdx.x;
     const int64_t wbeg = b * kSortBlockItems + (int64_t)warp * kSortWarpItems;
@@ -344,12 +351,14 @@ sort_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
         __syncwarp();
     }
     __syncthreads();
-    {   // thread t owns digit t: global base of this block for the digit, then running offsets per warp
-        uint32_t run = table[(int64_t)tid * nblocks + b];
+    // thread t owns digits t, t + 256, ...: global base of this block for the digit, then running offsets per warp
+#pragma unroll
+    for (int d = tid; d < RADIX; d += kSortThreads) {
+        uint32_t run = table[(int64_t)d * nblocks + b];
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = wbase[w][tid];
-            wbase[w][tid] = run;
+            uint32_t c = wbase[w][d];
+            wbase[w][d] = run;
             run += c;
         }
     }
@@ -374,13 +383,14 @@ sort_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
 }
 
 // Sort n 64-bit elements by bits [bit_lo, bit_lo + n_bits).  Ping-pongs between a and b; returns which
-// buffer holds the result through *result_in_b.  ws: sort_workspace_bytes(n).
+// buffer holds the result through *result_in_b.  ws: sort_workspace_bytes(n).  As few passes as 9-bit digits allow
+// (14 key bits: 7 + 7; 18 key bits: 9 + 9), 256 buckets whenever the digits of the pass fit 8 bits.
 inline cudaError_t radix_sort_u64(uint64_t *a, uint64_t *b, int64_t n, int bit_lo, int n_bits, void *ws, cudaStream_t s,
                                   int *result_in_b, int *launches = nullptr)
 {
     *result_in_b = 0;
     if (n <= 0 || n_bits <= 0) return cudaSuccess;
-    int passes = (n_bits + 7) / 8;
+    int passes = (n_bits + kRadixMaxBits - 1) / kRadixMaxBits;
     int per = (n_bits + passes - 1) / passes;
     uint32_t *table = (uint32_t *)ws;
     size_t toff = ((sort_table_entries(n) + 64) * sizeof(uint32_t) + 255) / 256 * 256;
@@ -392,10 +402,13 @@ inline cudaError_t radix_sort_u64(uint64_t *a, uint64_t *b, int64_t n, int bit_l
         int bits = (n_bits - done) < per ? (n_bits - done) : per;
         uint32_t mask = (1u << bits) - 1u;
         int shift = bit_lo + done;
-        sort_hist_kernel<<<(unsigned)nb, kSortWarps * 32, 0, s>>>(src, n, shift, mask, table, nb);
-        cudaError_t e = scan_exclusive<uint32_t>(table, nb * kRadix, scan_tmp, nullptr, s, launches);
+        const int radix = bits > 8 ? 512 : 256;
+        if (radix == 512) sort_hist_kernel<512><<<(unsigned)nb, kSortThreads, 0, s>>>(src, n, shift, mask, table, nb);
+        else sort_hist_kernel<256><<<(unsigned)nb, kSortThreads, 0, s>>>(src, n, shift, mask, table, nb);
+        cudaError_t e = scan_exclusive<uint32_t>(table, nb * radix, scan_tmp, nullptr, s, launches);
         if (e != cudaSuccess) return e;
-        sort_scatter_kernel<<<(unsigned)nb, kSortWarps * 32, 0, s>>>(src, dst, n, shift, mask, table, nb);
+        if (radix == 512) sort_scatter_kernel<512><<<(unsigned)nb, kSortThreads, 0, s>>>(src, dst, n, shift, mask, table, nb);
+        else sort_scatter_kernel<256><<<(unsigned)nb, kSortThreads, 0, s>>>(src, dst, n, shift, mask, table, nb);
         if (launches) *launches += 2;
         uint64_t *t = src; src = dst; dst = t;
         done += bits;

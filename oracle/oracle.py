@@ -146,8 +146,8 @@ def bin2d(pos, h, image_size, axis, x_min, x_max, y_min, y_max, tile=32, small_m
     res = dict(cls=cls.reshape(n_img, N), pairs=pairs, huge=huge)
     if sort:
         s = pairs.copy(); tmp = np.empty_like(s)
-        if npairs:
-            lib().orc_sort_pairs_stable(_p(s), C.c_int64(npairs), _p(tmp))
+        if npairs:      # stable by TILE key: the 4 image bits below it are not sorted on (pairs of a tile stay in emit order)
+            lib().orc_sort_pairs_stable_bits(_p(s), C.c_int64(npairs), _p(tmp), C.c_int(4 if n_img > 1 else 0))
         res["sorted"] = s
     return res
 
@@ -193,8 +193,8 @@ def bin3d(pos, h, grid_size, lo, hi, brick=8, small_max_vox=64, huge_min_bricks=
     lib().orc_bin3d(*args, _p(cls), _p(pairs), _p(huge), C.byref(nh))
     pairs = pairs[:npairs]; huge = huge[:nh.value]
     s = pairs.copy(); tmp = np.empty_like(s)
-    if npairs:
-        lib().orc_sort_pairs_stable(_p(s), C.c_int64(npairs), _p(tmp))
+    if npairs:          # stable by BRICK key: the 5 image bits below it are not sorted on
+        lib().orc_sort_pairs_stable_bits(_p(s), C.c_int64(npairs), _p(tmp), C.c_int(5 if n_img > 1 else 0))
     return dict(cls=cls.reshape(n_img, N), pairs=pairs, sorted=s, huge=huge)
 
 

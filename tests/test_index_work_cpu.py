@@ -113,6 +113,11 @@ def test_sorted_pairs_are_stable_by_key(oracle):
     key = (o["pairs"] >> np.uint64(32)).astype(np.int64)
     order = np.argsort(key, kind="stable")
     assert np.array_equal(o["sorted"], o["pairs"][order])
+    # periodic: the 4 image bits below the tile key are NOT sorted on -- within a tile the pairs stay in emit order
+    o = oracle.bin2d(pos, h, (128, 128), 2, 0.0, 10.0, 0.0, 10.0, small_max_px=4, periodic=True, box=(10.0, 10.0))
+    tile = (o["pairs"] >> np.uint64(36)).astype(np.int64)
+    assert np.array_equal(o["sorted"], o["pairs"][np.argsort(tile, kind="stable")])
+    assert len(np.unique((o["pairs"] >> np.uint64(32)) & np.uint64(15))) > 1          # several images do occur
 
 
 def test_contributor_count_matches_map_support(oracle):
