@@ -151,9 +151,9 @@ AST_HD Bin2 classify2(const Axis1 &ax, const Axis1 &ay, double pa, double pb, do
 
 // Enumerate the tiles of a CLS_TILED particle image in emit order (tx ascending, then ty ascending) and call
 // f(tile_key) for every tile that holds at least one pixel satisfying the 2-D mask.  Returns the count.
+// (the callback of the _xy form gets the tile coordinates instead of the key)
 template <int TILE, class F>
-AST_HD int for_each_tile2(const Axis1 &ax, const Axis1 &ay, double pa, double pb, double R2, const Bin2 &b,
-                          int nty, F &&f)
+AST_HD int for_each_tile2_xy(const Axis1 &ax, const Axis1 &ay, double pa, double pb, double R2, const Bin2 &b, F &&f)
 {
     int cnt = 0;
     for (int tx = b.tx0; tx <= b.tx1; ++tx) {
@@ -165,12 +165,19 @@ AST_HD int for_each_tile2(const Axis1 &ax, const Axis1 &ay, double pa, double pb
             int yb = ty * TILE + TILE - 1 < b.bb.y1 ? ty * TILE + TILE - 1 : b.bb.y1;
             double mdy = min_dist2(ay, pb, ya, yb);
             if (AST_DADD(mdx, mdy) < R2) {
-                f((uint32_t)(tx * nty + ty));
+                f(tx, ty);
                 ++cnt;
             }
         }
     }
     return cnt;
+}
+
+template <int TILE, class F>
+AST_HD int for_each_tile2(const Axis1 &ax, const Axis1 &ay, double pa, double pb, double R2, const Bin2 &b,
+                          int nty, F &&f)
+{
+    return for_each_tile2_xy<TILE>(ax, ay, pa, pb, R2, b, [&](int tx, int ty) { f((uint32_t)(tx * nty + ty)); });
 }
 
 // ---- 3-D voxel grid: bricks of BRICK^3 voxels, same canonical ranges per axis ----------------------------------
