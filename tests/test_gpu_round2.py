@@ -97,6 +97,11 @@ def test_large_h_split_on_a_big_image(oracle):
     img2, st3 = gpu_project(pos2, h2, prop2, (512, 512), 2, b, periodic=True, box=(1.0, 1.0), huge_min_tiles=16)
     assert st3["n_huge"] > 1000
     check(img2, ref2)
+    # the same through small windows: many large-h windows, several pair rounds in each
+    img3, st4 = gpu_project(pos2, h2, prop2, (512, 512), 2, b, periodic=True, box=(1.0, 1.0), huge_min_tiles=16, huge_capacity=64,
+                            pair_capacity=50_000)
+    assert st4["n_huge"] == st3["n_huge"] and st4["n_pairs"] == st3["n_pairs"] and st4["n_rounds"] > st4["n_huge"] // 64
+    check(img3, ref2)
 
 
 def test_large_h_pairs_bit_exact(oracle):
