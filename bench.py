@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-sub", action="store_true", help="skip the c2 / c4 / c5 sub-records")
     ap.add_argument("--sub", default="c5,c2,c4", help="which sub-records to run")
     ap.add_argument("--cpu-target-s", type=float, default=12.0)
+    ap.add_argument("--c5-full-n", type=int, default=1024, help="lattice size of the full-size config-5 record (8 GPUs, or --sub c5full)")
     return ap.parse_args()
 
 
@@ -318,6 +319,59 @@ def sub_c5(ctx, args, pos_all_d, peak):
     return rec
 
 
+def sub_c5_full(ctx, args, peak, n=1024):
+    """configs[4] as worded: k-NN (k = 48, periodic) on 1024^3 = 1.07e9 particles across the GPUs of the box.  Every rank
+    generates ITS index range of the jittered lattice on the device (x-planes, counter-free torch CUDA generator seeded per rank:
+    the set is reproducible per (n, world)), nothing is replicated: slabs + ghost zones, one all-to-all of positions, one of
+    results (distributed.smoothing_lengths_slabs).  Parity: h of a cube inside rank 0's slab against scipy on that cube + margin."""
+    import torch
+    import torch.distributed as dist
+    from astro_sph_tools_b200 import distributed as astd, synthetic
+    from astro_sph_tools_b200.tools.smoothing import SmoothingLengthSolver
+    k = args.k
+    N = n ** 3
+    planes = n // ctx.world
+    p0 = ctx.rank * planes
+    g = torch.Generator(device=ctx.dev); g.manual_seed(777 + ctx.rank)
+    ax = (torch.arange(n, dtype=torch.float64, device=ctx.dev) + 0.5) / n
+    pos = torch.empty((planes * n * n, 3), dtype=torch.float64, device=ctx.dev)
+    step = max(1, planes // 16)
+    for i0 in range(0, planes, step):                           # slab by slab: no slab-sized temporaries
+        i1 = min(planes, i0 + step)
+        blk = torch.stack(torch.meshgrid(ax[p0 + i0:p0 + i1], ax, ax, indexing="ij"), dim=-1).reshape(-1, 3)
+        blk = torch.remainder(blk + torch.randn(blk.shape, dtype=torch.float64, device=ctx.dev, generator=g) * (0.2 / n), 1.0)
+        blk[blk >= 1.0] = 0.0
+        pos[i0 * n * n:i1 * n * n] = blk
+    del blk
+    torch.cuda.empty_cache()
+    sol = SmoothingLengthSolver(device=ctx.dev)
+    f = lambda: astd.smoothing_lengths_slabs(pos, k, 1.0, solver=sol, return_stats=True)
+    ms = timed_device(ctx, f, 1, 1)
+    h, st = f()
+    rec = {"config": f"k-NN k={k} periodic, jittered lattice {n}^3 = {N} particles generated per rank on the device, slabs + ghost zones "
+                     f"over {ctx.world} GPUs (nothing replicated)",
+           "ms": ms, "queries_per_s": N / (ms * 1e-3), "n_gpus": ctx.world, "iterations": st["iterations"],
+           "ghost_fraction_rank0": st["ghost_fraction"], "local_set_rank0": st["local_set"],
+           "roofline": {"bound": "hbm", "achieved": N * 32 / (ms * 1e-3) / 1e9, "peak": peak * ctx.world, "unit": "GB/s",
+                        "frac": N * 32 / (ms * 1e-3) / 1e9 / (peak * ctx.world), "algorithmic_bytes": N * 32}}
+    if ctx.rank == 0:
+        from scipy.spatial import cKDTree
+        h_cap = 1.25 * synthetic.s1_h_lattice_estimate(n, k)
+        c = (0.5 + planes // 2) / n                               # a cube in the middle of rank 0's slab (x), box centre (y, z)
+        half = 12.0 / n
+        lo = torch.tensor([c - half, 0.5 - half, 0.5 - half], dtype=torch.float64, device=ctx.dev); hi = lo + 2 * half
+        near = ((pos > lo - h_cap) & (pos < hi + h_cap)).all(dim=1)
+        P = pos[near].cpu().numpy(); H = h[near].cpu().numpy()
+        inner = np.all((P > lo.cpu().numpy()) & (P < hi.cpu().numpy()), axis=1)
+        ref = cKDTree(P).query(P[inner], k=k, workers=-1)[0][:, k - 1]
+        ok = bool(ref.max() <= h_cap and np.array_equal(H[inner], ref)) if c - half - h_cap > 0 and c + half + h_cap < planes / n else None
+        rec["parity"] = {"bit_equal_to_scipy": ok, "queries": int(inner.sum()), "note": "cube of 24^3 lattice cells inside rank 0's slab + margin"}
+    sol._ws = None
+    del pos, h
+    torch.cuda.empty_cache()
+    return rec
+
+
 def sub_c2(ctx, args, peak):
     """configs[1]: S1 256^3 -> 2048^2 mass + temperature-weighted maps in one pass (round 1's headline workload)"""
     import torch
@@ -493,6 +547,7 @@ def main():
     want = [] if args.no_sub else [s for s in args.sub.split(",") if s]
     if "c5" in want:
         subs["c5"] = sub_c5(ctx, args, pos_all_d, peak)
+    run_c5_full = ("c5full" in want) or ("c5" in want and world == 8)
     sol._ws = None
     pos_d = pos_all_d[lo_i:hi_i].clone() if world > 1 else pos_all_d
     del pos_all_d
@@ -642,6 +697,12 @@ def main():
     del out, pos_d, m_d, h_loc_d
     eng._ws = None
     torch.cuda.empty_cache()
+    if run_c5_full:                                               # configs[4] at its full size, on the 8 GPUs of the box
+        try:
+            subs["c5_1024cubed"] = sub_c5_full(ctx, args, peak, args.c5_full_n)
+        except Exception as e:                                    # (every rank fails or none: the collectives inside stay matched)
+            subs["c5_1024cubed"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
     if world == 1:
         for name, fn in (("c2", sub_c2), ("c4", sub_c4)):
             if name in want:
