@@ -204,6 +204,66 @@ __global__ void __launch_bounds__(kBin3Threads, 3) emit3_kernel(P3 p, const uint
     }
 }
 
+// Large-h split (round 2, same as huge_tiles_kernel of project2d.cu): one WARP per entry of the large-h list enumerates the
+// entry's brick bbox 32 bricks at a time in emit order (bx, by, bz ascending) with the membership test of for_each_brick3.
+// WRITE = false: hoff[e] = number of member bricks.  WRITE = true: hoff holds the exclusive scan; pair number
+// g = base + hoff[e] + rank goes to pairs[g - w0] when it falls into the window [w0, w1).  Round 1 let EVERY brick walk and cull
+// the whole list (O(bricks x entries)).
+template <bool WRITE>
+__global__ void __launch_bounds__(256) huge_bricks_kernel(P3 p, const uint64_t *__restrict__ huge, uint32_t n_entries,
+                                                          uint64_t *__restrict__ hoff, uint64_t base, uint64_t w0, uint64_t w1,
+                                                          uint64_t *__restrict__ pairs)
+{
+    const uint32_t e = (uint32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= n_entries) return;                             // uniform for the warp
+    uint64_t g = 0;
+    if (WRITE) {
+        g = base + hoff[e];
+        const uint64_t gend = base + hoff[e + 1];
+        if (gend <= w0 || g >= w1) return;
+    }
+    const uint64_t ent = huge[e];
+    const int64_t i = (int64_t)(uint32_t)ent;
+    const int m = (int)(ent >> 32);
+    const double h = p.h[i], R2 = radius2(h);
+    const double q[3] = { AST_DADD(p.pos[3 * i], image_shift3(p.n_img, p.box, m, 0)), AST_DADD(p.pos[3 * i + 1], image_shift3(p.n_img, p.box, m, 1)),
+                          AST_DADD(p.pos[3 * i + 2], image_shift3(p.n_img, p.box, m, 2)) };
+    const Bin3 b = classify3<BRICK>(p.ax, q, h, R2, p.small_max_vox, p.huge_min_bricks);
+    const int ny_b = b.b1[1] - b.b0[1] + 1, nz_b = b.b1[2] - b.b0[2] + 1;
+    const int64_t nt = (int64_t)(b.b1[0] - b.b0[0] + 1) * ny_b * nz_b;
+    uint32_t cnt = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t t0 = 0; t0 < nt; t0 += 32) {
+        const int64_t t = t0 + lane;
+        bool in = false;
+        uint32_t key = 0;
+        if (t < nt) {
+            const int bz = b.b0[2] + (int)(t % nz_b), by = b.b0[1] + (int)((t / nz_b) % ny_b), bx = b.b0[0] + (int)(t / ((int64_t)nz_b * ny_b));
+            const int bc[3] = { bx, by, bz };
+            double md[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int a0 = bc[c] * BRICK > b.lo[c] ? bc[c] * BRICK : b.lo[c];
+                const int a1 = bc[c] * BRICK + BRICK - 1 < b.hi[c] ? bc[c] * BRICK + BRICK - 1 : b.hi[c];
+                md[c] = min_dist2(p.ax[c], q[c], a0, a1);
+            }
+            in = AST_DADD(AST_DADD(md[0], md[1]), md[2]) < R2;
+            key = (uint32_t)((bx * p.nb[1] + by) * p.nb[2] + bz);
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, in);
+        if (WRITE) {
+            const uint64_t gg = g + (uint64_t)__popc(ball & lt);
+            if (in && gg >= w0 && gg < w1)
+                pairs[gg - w0] = ((uint64_t)((key << p.img_shift) | (uint32_t)m) << 32) | (uint64_t)(uint32_t)i;
+            g += (uint64_t)__popc(ball);
+        } else {
+            cnt += (uint32_t)__popc(ball);
+        }
+    }
+    if (!WRITE && lane == 0) hoff[e] = (uint64_t)cnt;
+}
+
 static __global__ void brick_range_kernel(const uint64_t *__restrict__ sorted, int64_t n, int img_shift, uint32_t *__restrict__ tbeg,
                                           uint32_t *__restrict__ tend)
 {
@@ -243,8 +303,8 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
     TileWork w;
     if (!resolve_work(a, w)) return;
     const int brick = w.tile;
-    const uint32_t beg = w.beg, cnt = w.cnt;
-    const uint32_t total = cnt + w.n_huge;
+    const uint32_t beg = __shfl_sync(0xffffffffu, w.beg, 0), total = __shfl_sync(0xffffffffu, w.cnt, 0);   // uniform loop control
+    const uint32_t w_first = __shfl_sync(0xffffffffu, w.first, 0), w_step = __shfl_sync(0xffffffffu, w.step, 0);
     if (total == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bz = brick % a.nb[2], by = (brick / a.nb[2]) % a.nb[1], bx = brick / (a.nb[2] * a.nb[1]);
@@ -260,21 +320,13 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
     double acc64[4] = { 0.0, 0.0, 0.0, 0.0 };
     int since_fold = 0;
 
-    for (uint32_t base = w.first; base < total; base += w.step) {
+    for (uint32_t base = w_first; base < total; base += w_step) {
         const uint32_t j = base + lane;
         bool hit = false, outer = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f), S = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < total) {
-            uint32_t idx, m;
-            if (j < cnt) {
-                const uint64_t e = a.sorted[beg + j];
-                idx = (uint32_t)e;
-                m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
-            } else {
-                const uint64_t e = a.huge[j - cnt];
-                idx = (uint32_t)e;
-                m = (uint32_t)(e >> 32);
-            }
+            const uint64_t e = a.sorted[beg + j];
+            const uint32_t idx = (uint32_t)e, m = ((uint32_t)(e >> 32)) & ((1u << a.img_shift) - 1u);
             const Rec3 r = a.rec[idx];
             const float fx = (float)((r.x + image_shift3(a.n_img, a.box, (int)m, 0) - a.lo[0]) * a.inv_d[0] - (double)X0);
             const float fy = (float)((r.y + image_shift3(a.n_img, a.box, (int)m, 1) - a.lo[1]) * a.inv_d[1] - (double)Y0);
@@ -378,6 +430,7 @@ struct Layout3 {
     uint64_t *pmask;
     uint64_t *pairs_a, *pairs_b, *huge;
     uint32_t *tbeg, *tend, *seg_off, *seg_tmp;
+    uint64_t *hoff, *hoff_tmp;
     int *wexp;
     void *sort_ws;
     size_t bytes;
@@ -424,6 +477,8 @@ static Layout3 layout3(const ast_grid3d_params *p, void *ws)
     L.seg_off = c.take<uint32_t>(L.nbricks + 1);
     L.seg_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(L.nbricks + 1));
     L.wexp = c.take<int>(2);
+    L.hoff = c.take<uint64_t>(L.huge_cap + 1);
+    L.hoff_tmp = (uint64_t *)c.take<char>(scan_workspace_bytes<uint64_t>(L.huge_cap + 1));
     L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
     L.bytes = c.bytes();
     return L;
@@ -530,13 +585,10 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
         return AST_EWORKSPACE;
     }
     if (T + H > 0) {
-        // pair_capacity and huge_capacity are WINDOWS: the pairs are walked through the pair window in rounds, the large-h list
-        // through its window likewise (every brick walks the entries of the current window), so no capacity can fail after the
+        // pair_capacity and huge_capacity are WINDOWS: the combined pair order -- tiled pairs, then the member bricks of the
+        // current window of the large-h list -- is walked through the pair window in rounds, so no capacity can fail after the
         // binning kernel has deposited the few-voxel particles
         const uint64_t cap = (uint64_t)L.pair_cap, hcap = (uint64_t)L.huge_cap;
-        const uint64_t rounds = T ? (T + cap - 1) / cap : 0;
-        const uint64_t n_hwin = H ? (H + hcap - 1) / hcap : 0;
-        const uint64_t passes = rounds > n_hwin ? rounds : n_hwin;
         const int key_bits = ceil_log2_u64((uint64_t)L.nbricks);     // the image bits below the brick key are NOT sorted on
         Acc3 c;
         c.tbeg = L.tbeg; c.tend = L.tend; c.huge = L.huge; c.rec = L.rec; c.out = out;
@@ -547,44 +599,70 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
         c.n_img = a.n_img;
         c.tab = a.tab;
         c.wexp = L.wexp;
+        c.n_huge = 0u;
         for (int k = 0; k < 3; ++k) c.box[k] = a.box[k];
         static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
-        for (uint64_t r = 0; r < passes; ++r) {
-            // pass r: pair window r (if any left) together with large-h window r (if any left)
-            const uint64_t w0 = r < rounds ? r * cap : 0, w1 = r < rounds ? ((w0 + cap < T) ? w0 + cap : T) : 0;
-            const uint64_t h0 = r < n_hwin ? r * hcap : 0, h1 = r < n_hwin ? ((h0 + hcap < H) ? h0 + hcap : H) : 0;
-            const int64_t nw = (int64_t)(w1 - w0);
-            tk.begin(2);
-            emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, w0, w1, L.pairs_a, L.huge, h0, h1);
-            tk.end();
-            int in_b = 0, nl = 0;
-            tk.begin(3);
-            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32 + a.img_shift, key_bits, L.sort_ws, s, &in_b, &nl));
-            tk.end();
-            tk.begin(4);
-            AST_CUDA_TRY(cudaMemsetAsync(L.tbeg, 0, sizeof(uint32_t) * L.nbricks, s));
-            AST_CUDA_TRY(cudaMemsetAsync(L.tend, 0, sizeof(uint32_t) * L.nbricks, s));
-            c.sorted = in_b ? L.pairs_b : L.pairs_a;
-            if (nw > 0) brick_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
-            tk.end();
-            c.n_huge = (uint32_t)(h1 - h0);
-            // work items: long brick lists (cluster cores) are shared by several CTAs, see work_items.cuh
-            const uint32_t seg_target = segment_target(nw, (int64_t)sm_count * 8);
-            c.seg_off = L.seg_off; c.ntiles = (int)L.nbricks;
-            tile_segments_kernel<<<(unsigned)((L.nbricks + 1 + 255) / 256), 256, 0, s>>>(L.tbeg, L.tend, c.n_huge, seg_target, (int)L.nbricks,
-                                                                                     L.seg_off);
-            int nls = 0;
-            AST_CUDA_TRY(scan_exclusive<uint32_t>(L.seg_off, L.nbricks + 1, L.seg_tmp, nullptr, s, &nls));
-            const int64_t max_items = L.nbricks + nw / (int64_t)seg_target;
-            tk.begin(5);
-            if (a.shape == SHAPE_CUBIC) brick_accum_kernel<SHAPE_CUBIC><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
-            else if (a.shape == SHAPE_WENDLAND) brick_accum_kernel<SHAPE_WENDLAND><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
-            else brick_accum_kernel<SHAPE_TABLE><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
-            tk.end();
-            st.n_launches += 4 + nl + nls;
-            AST_CUDA_TRY(cudaGetLastError());
+        int64_t round_no = 0;
+        const uint64_t n_hwin = H ? (H + hcap - 1) / hcap : 1;
+        for (uint64_t hw = 0; hw < n_hwin; ++hw) {
+            uint64_t HP = 0;
+            uint32_t n_hent = 0;
+            if (H) {                    // the large-h window: list entries [h0, h1) -> member-brick counts -> offsets
+                const uint64_t h0 = hw * hcap, h1 = (h0 + hcap < H) ? h0 + hcap : H;
+                n_hent = (uint32_t)(h1 - h0);
+                tk.begin(2);
+                emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, 0, L.pairs_a, L.huge, h0, h1);
+                AST_CUDA_TRY(cudaMemsetAsync(L.hoff + n_hent, 0, sizeof(uint64_t), s));
+                huge_bricks_kernel<false><<<(n_hent + 7) / 8, 256, 0, s>>>(a, L.huge, n_hent, L.hoff, 0, 0, 0, nullptr);
+                int nlh = 0;
+                AST_CUDA_TRY(scan_exclusive<uint64_t>(L.hoff, (int64_t)n_hent + 1, L.hoff_tmp, nullptr, s, &nlh));
+                st.n_launches += 2 + nlh;
+                tk.end();
+                AST_CUDA_TRY(cudaMemcpyAsync(&HP, L.hoff + n_hent, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+                AST_CUDA_TRY(cudaStreamSynchronize(s));
+                st.n_pairs += (int64_t)HP;
+            }
+            const uint64_t base = hw == 0 ? T : 0, total = base + HP;
+            if (total == 0) continue;
+            const uint64_t rounds = (total + cap - 1) / cap;
+            uint64_t per_round = rounds > 1 ? (((total + rounds - 1) / rounds + 8191ull) & ~8191ull) : cap;
+            if (per_round > cap) per_round = cap;
+            for (uint64_t r = 0; r * per_round < total; ++r, ++round_no) {
+                const uint64_t w0 = r * per_round, w1 = (w0 + per_round < total) ? w0 + per_round : total;
+                const int64_t nw = (int64_t)(w1 - w0);
+                tk.begin(2);
+                if (hw == 0 && w0 < T)
+                    emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, w0, w1 < T ? w1 : T, L.pairs_a, L.huge, 0, 0);
+                if (HP > 0 && w1 > base)
+                    huge_bricks_kernel<true><<<(n_hent + 7) / 8, 256, 0, s>>>(a, L.huge, n_hent, L.hoff, base, w0, w1, L.pairs_a);
+                tk.end();
+                int in_b = 0, nl = 0;
+                tk.begin(3);
+                AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, nw, 32 + a.img_shift, key_bits, L.sort_ws, s, &in_b, &nl));
+                tk.end();
+                tk.begin(4);
+                AST_CUDA_TRY(cudaMemsetAsync(L.tbeg, 0, sizeof(uint32_t) * L.nbricks, s));
+                AST_CUDA_TRY(cudaMemsetAsync(L.tend, 0, sizeof(uint32_t) * L.nbricks, s));
+                c.sorted = in_b ? L.pairs_b : L.pairs_a;
+                brick_range_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(c.sorted, nw, a.img_shift, L.tbeg, L.tend);
+                tk.end();
+                // work items: long brick lists (cluster cores) are shared by several CTAs, see work_items.cuh
+                const uint32_t seg_target = segment_target(nw, (int64_t)sm_count * 8);
+                c.seg_off = L.seg_off; c.ntiles = (int)L.nbricks;
+                tile_segments_kernel<<<(unsigned)((L.nbricks + 1 + 255) / 256), 256, 0, s>>>(L.tbeg, L.tend, 0u, seg_target, (int)L.nbricks, L.seg_off);
+                int nls = 0;
+                AST_CUDA_TRY(scan_exclusive<uint32_t>(L.seg_off, L.nbricks + 1, L.seg_tmp, nullptr, s, &nls));
+                const int64_t max_items = L.nbricks + nw / (int64_t)seg_target;
+                tk.begin(5);
+                if (a.shape == SHAPE_CUBIC) brick_accum_kernel<SHAPE_CUBIC><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
+                else if (a.shape == SHAPE_WENDLAND) brick_accum_kernel<SHAPE_WENDLAND><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
+                else brick_accum_kernel<SHAPE_TABLE><<<(unsigned)max_items, kAcc3Threads, 0, s>>>(c);
+                tk.end();
+                st.n_launches += 6 + nl + nls;
+                AST_CUDA_TRY(cudaGetLastError());
+            }
         }
-        st.n_rounds = (int64_t)passes;
+        st.n_rounds = round_no;
     }
     tm.end();
     if (timing) {
@@ -627,22 +705,38 @@ extern "C" int ast_bin3d(const ast_grid3d_params *p, const double *pos, const do
         AST_CUDA_TRY(cudaMemcpyAsync(&totals[1], L.block_huge + L.nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         AST_CUDA_TRY(cudaStreamSynchronize(s));
     }
-    if (counts) { counts[0] = (int64_t)totals[0]; counts[1] = (int64_t)totals[1]; }
-    if (totals[0] > (uint64_t)p->pair_capacity || totals[1] > (uint64_t)p->huge_capacity) {
-        set_error("capacity too small: need %llu pairs and %llu huge entries", (unsigned long long)totals[0],
-                  (unsigned long long)totals[1]);
+    const uint64_t T = totals[0], H = totals[1];
+    uint64_t HP = 0;
+    if (H > (uint64_t)p->huge_capacity || H > (uint64_t)L.huge_cap) {
+        if (counts) { counts[0] = (int64_t)T; counts[1] = (int64_t)H; }
+        set_error("capacity too small: need %llu huge entries", (unsigned long long)H);
         return AST_EWORKSPACE;
     }
-    if (totals[0] + totals[1] > 0) {
-        emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, totals[0], L.pairs_a, L.huge, 0,
-                                                            totals[1]);
+    if (H > 0) {
+        const uint32_t nh = (uint32_t)H;
+        emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, 0, L.pairs_a, L.huge, 0, H);
+        AST_CUDA_TRY(cudaMemsetAsync(L.hoff + nh, 0, sizeof(uint64_t), s));
+        huge_bricks_kernel<false><<<(nh + 7) / 8, 256, 0, s>>>(a, L.huge, nh, L.hoff, 0, 0, 0, nullptr);
+        AST_CUDA_TRY(scan_exclusive<uint64_t>(L.hoff, (int64_t)nh + 1, L.hoff_tmp, nullptr, s));
+        AST_CUDA_TRY(cudaMemcpyAsync(&HP, L.hoff + nh, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        AST_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    const uint64_t total = T + HP;
+    if (counts) { counts[0] = (int64_t)total; counts[1] = (int64_t)H; }
+    if (total > (uint64_t)p->pair_capacity) {
+        set_error("capacity too small: need %llu pairs and %llu huge entries", (unsigned long long)total, (unsigned long long)H);
+        return AST_EWORKSPACE;
+    }
+    if (total + H > 0) {
+        if (T > 0) emit3_kernel<<<(unsigned)L.nb, kBin3Threads, 0, s>>>(a, L.block_pairs, L.block_huge, 0, T, L.pairs_a, L.huge, 0, 0);
+        if (HP > 0) huge_bricks_kernel<true><<<((uint32_t)H + 7) / 8, 256, 0, s>>>(a, L.huge, (uint32_t)H, L.hoff, T, 0, total, L.pairs_a);
         AST_CUDA_TRY(cudaGetLastError());
-        if (huge && totals[1]) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * totals[1], cudaMemcpyDeviceToDevice, s));
-        if (pairs_sorted && totals[0]) {
+        if (huge && H) AST_CUDA_TRY(cudaMemcpyAsync(huge, L.huge, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, s));
+        if (pairs_sorted && total) {
             int in_b = 0;
             const int key_bits = ceil_log2_u64((uint64_t)L.nbricks);
-            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, (int64_t)totals[0], 32 + a.img_shift, key_bits, L.sort_ws, s, &in_b));
-            AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? L.pairs_b : L.pairs_a, sizeof(uint64_t) * totals[0],
+            AST_CUDA_TRY(radix_sort_u64(L.pairs_a, L.pairs_b, (int64_t)total, 32 + a.img_shift, key_bits, L.sort_ws, s, &in_b));
+            AST_CUDA_TRY(cudaMemcpyAsync(pairs_sorted, in_b ? L.pairs_b : L.pairs_a, sizeof(uint64_t) * total,
                                          cudaMemcpyDeviceToDevice, s));
         }
     }

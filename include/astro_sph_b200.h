@@ -148,9 +148,10 @@ typedef struct ast_grid3d_params {
     double lo[3], hi[3];
     double box[3];
     int64_t small_max_vox;       /* bbox volume up to which a particle is deposited directly; <0 = default */
-    int64_t huge_min_bricks;     /* brick-bbox count above which a particle goes to the global list; <0 = default */
-    int64_t pair_capacity;
-    int64_t huge_capacity;
+    int64_t huge_min_bricks;     /* brick-bbox count above which a particle image goes on the large-h list and is split across its
+                                    bricks by a warp of its own (huge_bricks_kernel); <0 = default */
+    int64_t pair_capacity;       /* WINDOW of (brick, particle) pairs, as in ast_project2d_params */
+    int64_t huge_capacity;       /* WINDOW of large-h list entries */
     const float *kernel_table;   /* as in ast_project2d_params */
     int32_t kernel_table_n;
     int32_t kernel_dim;
@@ -162,7 +163,9 @@ int ast_grid3d(const ast_grid3d_params *p, const double *pos, const double *h, c
 
 /* 3-D index work for the bit-exact parity tests: bbox n_img*N*6 int32 (x0,x1,y0,y1,z0,z1), cls n_img*N uint8,
  * pairs_sorted pair_capacity uint64 = (sort_key << 32) | particle with sort_key = brick_key * (periodic ? 32 : 1) + image,
- * brick_key = (bx*nby + by)*nbz + bz; huge = (image << 32) | particle; counts (host) = {pairs, huge}.  Synchronises. */
+ * brick_key = (bx*nby + by)*nbz + bz, sorted (stably) by brick_key only; the tiled pairs are followed by the member bricks
+ * of the large-h entries (list order; bx, by, bz ascending); huge = (image << 32) | particle; counts (host) = {pairs (large-h
+ * pairs included), large-h entries}.  Here the capacities are limits.  Synchronises. */
 int ast_bin3d(const ast_grid3d_params *p, const double *pos, const double *h, int32_t *bbox, uint8_t *cls,
               uint64_t *pairs_sorted, uint64_t *huge, int64_t *counts, void *workspace, size_t workspace_bytes,
               void *stream);
