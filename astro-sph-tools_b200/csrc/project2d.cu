@@ -493,13 +493,16 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
                                                            uint64_t *__restrict__ pairs, uint64_t *__restrict__ huge,
                                                            uint64_t h0, uint64_t h1)
 {
+    constexpr int kStage = 512;                             // pairs staged per warp and round
     __shared__ uint32_t sm[34];
+    __shared__ uint64_t sbuf[kBinThreads / 32][kStage];
     const uint64_t pbase = pairs_excl[blockIdx.x], pnext = pairs_excl[blockIdx.x + 1];
     const uint64_t hbase = huge_excl[blockIdx.x], hnext = huge_excl[blockIdx.x + 1];
     const bool any_pairs = pnext > pbase && pnext > w0 && pbase < w1;
     const bool any_huge = hnext > hbase && hnext > h0 && hbase < h1;
     if (!any_pairs && !any_huge) return;                    // uniform for the block
     const int64_t i = (int64_t)blockIdx.x * kBinThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // counts and image masks come from K1 (it wrote them for every block that has entries): one enumeration here, not two
     uint32_t npairs = 0, nhuge = 0, mask = 0;
     if (i < p.n) {
@@ -510,25 +513,48 @@ __global__ void __launch_bounds__(kBinThreads) emit_kernel(P2 p, const uint64_t 
     uint32_t tot;
     uint64_t g = pbase + block_excl_scan_u32(npairs, sm, &tot);
     uint64_t gh = hbase + block_excl_scan_u32(nhuge, sm, &tot);
-    if (i >= p.n || (npairs == 0 && nhuge == 0)) return;
     if (!any_pairs) mask &= 0xffff0000u;                    // only the large-h entries are wanted
     if (!any_huge) mask &= 0x0000ffffu;
-    if (mask == 0u) return;
-    if (mask & 0x8000u) {
-        // single image whose member tiles K1 stored: no geometry here, just the set bits in emit order (tx, then ty ascending)
-        uint64_t tm = p.ptmask[i];
-        const uint64_t org = p.ptorg[i];
-        const int tx0 = (int)(org & 0xffffffu), ty0 = (int)((org >> 24) & 0xffffffu), rows = (int)(org >> 48);
-        while (tm) {
-            const int bit = __ffsll((long long)tm) - 1;
-            tm &= tm - 1ull;
-            const int dx = bit / rows, dy = bit - dx * rows;
-            if (g >= w0 && g < w1)
-                pairs[g - w0] = ((uint64_t)(uint32_t)((tx0 + dx) * p.nty + ty0 + dy) << 32) | (uint64_t)(uint32_t)i;
-            ++g;
+    // Single-image particles whose member tiles K1 stored (the bulk): no geometry here, just the set bits of the mask in emit
+    // order (tx, then ty ascending).  A thread's pairs are consecutive in the output, neighbouring threads' ranges adjoin: the
+    // warp's pairs form ONE contiguous range.  Written straight from the threads that is an 8-byte store to 32 different
+    // sectors per instruction; staged through the warp's shared-memory window the range goes out in full sectors
+    // (6.6 -> 5.9 ms at config 3).
+    const bool staged = (mask & 0x8000u) != 0u;
+    if (__any_sync(0xffffffffu, staged)) {
+        const uint64_t warp_base = __shfl_sync(0xffffffffu, g, 0);
+        const uint32_t warp_total = (uint32_t)(__shfl_sync(0xffffffffu, g + npairs, 31) - warp_base);
+        const uint32_t rel = (uint32_t)(g - warp_base);
+        uint64_t tm = 0, org = 0;
+        if (staged) { tm = p.ptmask[i]; org = p.ptorg[i]; }
+        const int tx0 = (int)(org & 0xffffffu), ty0 = (int)((org >> 24) & 0xffffffu), rows = staged ? (int)(org >> 48) : 1;
+        uint64_t *buf = sbuf[warp];
+        for (uint32_t c0 = 0; c0 < warp_total; c0 += kStage) {
+            for (int o = lane; o < kStage; o += 32) buf[o] = ~0ull;                 // slots of threads that write their own pairs
+            __syncwarp();
+            if (staged && rel < c0 + kStage && rel + npairs > c0) {
+                uint64_t t = tm;
+                uint32_t pos = rel;
+                while (t) {
+                    const int bit = __ffsll((long long)t) - 1;
+                    t &= t - 1ull;
+                    if (pos >= c0 && pos < c0 + kStage) {
+                        const int dx = bit / rows, dy = bit - dx * rows;
+                        buf[pos - c0] = ((uint64_t)(uint32_t)((tx0 + dx) * p.nty + ty0 + dy) << 32) | (uint64_t)(uint32_t)i;
+                    }
+                    ++pos;
+                }
+            }
+            __syncwarp();
+            const uint32_t nc = warp_total - c0 < (uint32_t)kStage ? warp_total - c0 : (uint32_t)kStage;
+            for (uint32_t o = lane; o < nc; o += 32) {
+                const uint64_t v = buf[o], gp = warp_base + c0 + o;
+                if (v != ~0ull && gp >= w0 && gp < w1) pairs[gp - w0] = v;
+            }
+            __syncwarp();
         }
-        return;
     }
+    if (i >= p.n || staged || mask == 0u) return;
     const double pa0 = p.pos[3 * i + p.a_col], pb0 = p.pos[3 * i + p.b_col], h = p.h[i], R2 = radius2(h);
     for (int m = 0; m < p.n_img; ++m) {
         if (!((mask >> m) & 0x10001u)) continue;                           // image m has neither pairs nor a large-h entry
