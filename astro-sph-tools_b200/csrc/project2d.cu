@@ -627,17 +627,6 @@ __global__ void __launch_bounds__(256) huge_tiles_kernel(P2 p, const uint64_t *_
     if (!WRITE && lane == 0) hoff[e] = (uint64_t)cnt;
 }
 
-// K5: first / one-past-last sorted pair of every tile (arrays pre-zeroed)
-__global__ void tile_range_kernel(const uint64_t *__restrict__ sorted, int64_t n, int img_shift, uint32_t *__restrict__ tbeg,
-                                  uint32_t *__restrict__ tend)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t t = (uint32_t)(sorted[i] >> 32) >> img_shift;
-    if (i == 0 || ((uint32_t)(sorted[i - 1] >> 32) >> img_shift) != t) tbeg[t] = (uint32_t)i;
-    if (i == n - 1 || ((uint32_t)(sorted[i + 1] >> 32) >> img_shift) != t) tend[t] = (uint32_t)(i + 1);
-}
-
 // K6
 struct Acc {
     const uint64_t *sorted;
@@ -658,7 +647,7 @@ struct Acc {
     const int *wexp;              // [AST_MAX_PROPS] the float32 weights are relative to 2^wexp[k] (see split_weight)
 };
 
-// K5 (default): the same first/last bookkeeping, and every sorted pair is turned into the two things the accumulate kernel
+// K5: first / one-past-last sorted pair of every tile (arrays pre-zeroed), and every sorted pair is turned into the two things the accumulate kernel
 // needs -- tile-relative float32 coordinates {fx, fy, sx, sy} and the weights -- ONCE, here.  The accumulate kernel used to do
 // this for every pair in each of its 8 warps (sorted pair -> dependent 32-byte record gather -> float64 arithmetic): 10 % of
 // its instructions and 19 % of its stall samples (ncu source view, profiles/r01_v4_summary.md).  Same expressions, same values.
