@@ -147,3 +147,30 @@ def test_grid_capacities_are_windows_and_weights_keep_float64_range(oracle):
             got, _ = gpu_grid(pos, h, prop * scale, size, lo, hi, **kw)
             assert np.isfinite(got).all()
             assert rel_l2(got / scale, ref) <= 1e-5 and abs((got / scale).sum() - ref.sum()) <= 1e-6 * np.abs(ref).sum()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_grids_through_random_windows(oracle, seed):
+    """random clouds, random grid shapes, periodic or not, random pair / large-h windows and class thresholds: the large-h split
+    (a warp per entry enumerates its bricks) and the rounds over both windows give the oracle's grid"""
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(200, 2500))
+    size = tuple(int(v) for v in rng.integers(9, 40, 3))
+    lo = tuple(rng.uniform(-0.1, 0.2, 3)); hi = tuple(np.array(lo) + rng.uniform(0.6, 1.1, 3))
+    pos = rng.uniform(0.0, 1.0, (n, 3))
+    vox = max((hi[c] - lo[c]) / size[c] for c in range(3))
+    h = np.exp(rng.uniform(np.log(0.1 * vox), np.log(8 * vox), n))
+    h[rng.random(n) < 0.03] = 0.0
+    prop = rng.normal(size=n)
+    periodic = bool(rng.random() < 0.4)
+    box = (1.0, 1.0, 1.0) if periodic else None
+    kw = dict(pair_capacity=int(rng.choice([300, 5000, 200_000])), huge_capacity=int(rng.choice([1, 5, 500])),
+              huge_min_bricks=int(rng.choice([0, 2, 30, 512])), small_max_vox=int(rng.choice([1, 27, 200])))
+    ref = oracle.grid3d(pos, h, prop, size, lo, hi, periodic=periodic, box=box)
+    g, st = gpu_grid(pos, h, prop, size, lo, hi, periodic=periodic, box=box, **kw)
+    if np.abs(ref).sum() == 0:
+        assert not g.any()
+        return
+    tol = (1e-5, 1e-6) if kw["small_max_vox"] >= 8 else (1e-4, 2e-5)       # sub-voxel particles forced through the brick path
+    assert rel_l2(g, ref) <= tol[0], (seed, kw, st)
+    assert abs(g.sum() - ref.sum()) <= tol[1] * np.abs(ref).sum(), (seed, kw, st)
