@@ -31,7 +31,7 @@ class SmoothingLengthSolver:
         self._lock = threading.RLock()        # one workspace: calls on this solver serialise
 
     def solve(self, pos, k=DEFAULT_K, box_size=None, q_begin=0, q_count=0, want_neighbours=False, want_distances=False,
-              stream=None, kernel="lockstep", full_build=False):
+              stream=None, kernel="lockstep", full_build=False, cell_target=None):
         """pos: (N,3) float64 CUDA tensor.  Returns h (Q,) [, idx (Q,k) int32] [, dist (Q,k)] as CUDA tensors where
         Q = q_count or N.  Multi-GPU use: every rank passes all positions and its own [q_begin, q_begin+q_count)."""
         torch = self.torch
@@ -51,7 +51,9 @@ class SmoothingLengthSolver:
             mn, mx = float(pos.min()), float(pos.max())
             if not (mn >= 0.0 and mx < p.box):
                 raise ValueError("periodic k-NN needs 0 <= x < box_size (scipy boxsize semantics)")
-        p.cell_target = self.cell_target
+        # mean particles per cell if the set filled the whole box; a caller whose set fills a fraction f of it (a slab of a
+        # multi-GPU decomposition) passes 2 f to keep ~2 particles per OCCUPIED cell
+        p.cell_target = float(cell_target) if cell_target else self.cell_target
         p.q_begin = int(q_begin); p.q_count = int(q_count)
         nq = int(q_count) if q_count and q_count > 0 else n
         need = C.c_size_t(0)

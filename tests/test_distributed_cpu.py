@@ -75,6 +75,7 @@ class _ScipySolver:
     """stands in for SmoothingLengthSolver on the CPU (the oracle's scipy call): only the sharding logic is under test"""
     def solve(self, pos, k, box_size=None, q_begin=0, q_count=0, **kw):
         import oracle
+        assert set(kw) <= {"cell_target"}
         h = oracle.knn_scipy(pos.numpy(), k, box_size)[0]
         return torch.from_numpy(h[q_begin:q_begin + q_count] if q_count else h)
 
