@@ -1174,7 +1174,7 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
         if (grid > n_full) grid = n_full;                                                                               \
         kern<<<(unsigned)grid, kBinThreads, smem, s>>>(__VA_ARGS__);                                                    \
     } while (0)
-    // measured on K1 alone (benchmarks/bin_probe.py, 512^3 particles with sub-pixel supports; stages x CTAs per SM): 2 x 3
+    // measured on K1 alone (512^3 particles with sub-pixel supports; stages x CTAs per SM): 2 x 3
     // (80 registers) 1.581 ms, 4 x 3: 1.587, 2 x 4 (64 registers, no spills): 1.469, 4 x 4: 1.488, 2 x 5 (48 registers,
     // spills): 1.608, 2 x 6: 2.000 -- occupancy, not pipeline depth, hides the latency; hence K0.  With SPH-realistic supports
     // the 80-register build of K1 is the faster one (7.18 against 7.69 ms at config 3).
