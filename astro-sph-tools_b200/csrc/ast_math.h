@@ -108,6 +108,11 @@ __device__ __forceinline__ float shape_half_full(float s, const ShapeTab &tab)
     }
     return shape_eval<SHAPE>(q, tab);
 }
+// cubic spline, inner region only (every q < 1): f/2 = 1/2 + s (3q/8 - 3/4)   (_kernels.pyx:17, halved)
+__device__ __forceinline__ float shape_half_inner(float s)
+{
+    return fmaf(s, fmaf(0.375f, fast_sqrt(s), -0.75f), 0.5f);
+}
 // cubic spline, outer annulus only (every q >= 1): f/2 = sat(1 - q/2)^3
 __device__ __forceinline__ float shape_half_outer(float s)
 {

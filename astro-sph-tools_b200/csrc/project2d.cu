@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
     int since_fold = 0;
     for (uint32_t base = w_first; base < total; base += w_step) {
         const uint32_t j = base + lane;
-        bool hit = false, outer = false;
+        bool hit = false, outer = false, inner = false;
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 C = make_float2(0.f, 0.f);
         if (j < total) {
@@ -738,14 +738,21 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
             const float qmin2 = ddx * ddx + ddy * ddy;
             hit = qmin2 < 4.0001f;
             outer = hit && SHAPE == SHAPE_CUBIC && qmin2 >= 1.0f;
+            if (SHAPE == SHAPE_CUBIC) {
+                // farthest pixel of the sub-tile: if even that one has q < 1 every pixel takes the inner branch alone
+                const float fdx = fmaxf(fx - lox, hix - fx) * sx, fdy = fmaxf(fy - loy, hiy - fy) * sy;
+                inner = hit && (fdx * fdx + fdy * fdy < 0.9999f);
+            }
             P = make_float4(fx * sx, fy * sy, sx, sy);
         }
-        const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
+        // slots: mixed hits from the front, then inner-only hits, outer-annulus hits from the back
+        const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer && !inner);
         const unsigned ball_o = __ballot_sync(0xffffffffu, outer);
-        const int nf = __popc(ball_f), no = __popc(ball_o), nh = nf + no;
+        const unsigned ball_i = SHAPE == SHAPE_CUBIC ? __ballot_sync(0xffffffffu, inner) : 0u;
+        const int nf = __popc(ball_f), no = __popc(ball_o), ni = __popc(ball_i), nh = nf + no + ni;
         if (nh == 0) continue;
         const unsigned lt = (1u << lane) - 1u;
-        const int dst = outer ? 31 - __popc(ball_o & lt) : __popc(ball_f & lt);
+        const int dst = outer ? 31 - __popc(ball_o & lt) : (inner ? nf + __popc(ball_i & lt) : __popc(ball_f & lt));
         if (nh >= kRowColMinHits) {
             if (hit) {
                 RowColSlot *d = slots + dst;
@@ -775,6 +782,18 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
                 }
             }
             if (SHAPE == SHAPE_CUBIC) {
+                for (int e = nf; e < nf + ni; ++e) {            // every pixel of the sub-tile has q < 1: f/2 = 1/2 + s (3q/8 - 3/4)
+                    const float2 ax2 = reinterpret_cast<const float2 *>(slots[e].ax)[lane >> 3];
+                    const float4 bc = slots[e].byc[lane & 7];
+                    const float f00 = shape_half_inner(ax2.x + bc.x), f01 = shape_half_inner(ax2.x + bc.y);
+                    const float f10 = shape_half_inner(ax2.y + bc.x), f11 = shape_half_inner(ax2.y + bc.y);
+                    acc[0][0] = fmaf(bc.z, f00, acc[0][0]); acc[0][1] = fmaf(bc.z, f01, acc[0][1]);
+                    acc[0][2] = fmaf(bc.z, f10, acc[0][2]); acc[0][3] = fmaf(bc.z, f11, acc[0][3]);
+                    if (NP > 1) {
+                        acc[NP - 1][0] = fmaf(bc.w, f00, acc[NP - 1][0]); acc[NP - 1][1] = fmaf(bc.w, f01, acc[NP - 1][1]);
+                        acc[NP - 1][2] = fmaf(bc.w, f10, acc[NP - 1][2]); acc[NP - 1][3] = fmaf(bc.w, f11, acc[NP - 1][3]);
+                    }
+                }
                 for (int e = 32 - no; e < 32; ++e) {
                     const float2 ax2 = reinterpret_cast<const float2 *>(slots[e].ax)[lane >> 3];
                     const float4 bc = slots[e].byc[lane & 7];
@@ -796,7 +815,7 @@ __global__ void __launch_bounds__(256, 3) rowcol_accum_kernel(Acc a)
             __syncwarp();
             // sparse batch: full and outer-annulus hits alike through the general shape
             for (int e = 0; e < nh; ++e) {
-                const int sl = e < nf ? e : 32 - nh + e;
+                const int sl = e < nf + ni ? e : 32 - nh + e;
                 const float4 q = slots[sl].ax[0];
                 const float2 c = *reinterpret_cast<const float2 *>(&slots[sl].ax[1]);
                 float ax2[PX], by2[PY];
