@@ -142,6 +142,31 @@ def test_config3_full_size_window_against_oracle(config3, oracle):
     torch.cuda.empty_cache()
 
 
+def test_more_than_2_to_the_32_pairs(config3, oracle):
+    """the 134 M particles with 2.5 x h: 5e9 (tile, particle) pairs -- beyond 32 bits.  Global emit indices are 64-bit, the pair
+    window (2^30) is indexed with 32 bits; five rounds.  Window of the map against the oracle."""
+    import torch
+    import bench
+    from astro_sph_tools_b200 import CoordinateAxes
+    from astro_sph_tools_b200.tools.projections import Projector2D
+    pos_d, h_d, idx, col = config3
+    N, npix, wp = pos_d.shape[0], 4096, 128
+    m_d = torch.full((N,), 1.0 / N, dtype=torch.float64, device="cuda")
+    h_big = h_d * 2.5
+    eng = Projector2D()
+    out = eng.project(pos_d, h_big, m_d, (npix, npix), CoordinateAxes.Z, (0.0, 1.0, 0.0, 1.0))
+    st = eng.last_stats
+    assert st["n_pairs"] > (1 << 32) and st["n_rounds"] >= 5
+    p0, lo, hi = bench.window_bounds(npix, wp)
+    h_col = h_big[torch.from_numpy(idx).cuda()].cpu().numpy()
+    sel = bench.select_column(col, lo, hi, 2.0 * h_col.max())
+    assert lo - 2.0 * h_col.max() > 0.42 and hi + 2.0 * h_col.max() < 0.62
+    ref = oracle.project2d(col[sel], h_col[sel], np.full(int(sel.sum()), 1.0 / N), (wp, wp), 2, lo, hi, lo, hi)
+    _window_check(out[p0:p0 + wp, p0:p0 + wp].cpu().numpy(), ref)
+    del out, eng
+    torch.cuda.empty_cache()
+
+
 def test_config5_knn_512cubed_subvolume_against_scipy(config3):
     """smoothing lengths of the 512^3 set (what configs[4] computes per GPU) against scipy on a sub-volume with margin"""
     import torch
