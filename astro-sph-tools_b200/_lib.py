@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ASTSPH_B200_LIB", os.path.join(_HERE, "csrc", "libastsph_b200.so"))
 
 AST_OK, AST_EINVAL, AST_EWORKSPACE, AST_ECUDA, AST_EUNSUPPORTED = 0, 1, 2, 3, 4
-FLAG_PERIODIC, FLAG_ACCUMULATE, FLAG_TIMING = 1, 2, 4
+FLAG_PERIODIC, FLAG_ACCUMULATE, FLAG_TIMING, FLAG_ORDER_AUTO, FLAG_ORDER_ALWAYS = 1, 2, 4, 8, 16
 MAX_PROPS = 2
 TILE = 32
 
@@ -30,7 +30,7 @@ class Project2DParams(C.Structure):
 
 class Project2DStats(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_huge", C.c_int64), ("n_rounds", C.c_int64), ("n_launches", C.c_int64),
-                ("stage_ms", C.c_float * 8)]
+                ("stage_ms", C.c_float * 8), ("reordered", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Grid3DParams(C.Structure):

@@ -12,6 +12,7 @@
 #include "ast_math.h"
 #include "block_utils.cuh"
 #include "common.cuh"
+#include "presort.cuh"
 #include "scan_sort.cuh"
 #include "work_items.cuh"
 
@@ -433,6 +434,7 @@ struct Layout3 {
     uint64_t *hoff, *hoff_tmp;
     int *wexp;
     void *sort_ws;
+    PresortBuffers pre;          // only with AST_FLAG_ORDER_AUTO / _ALWAYS
     size_t bytes;
 };
 
@@ -480,6 +482,18 @@ static Layout3 layout3(const ast_grid3d_params *p, void *ws)
     L.hoff = c.take<uint64_t>(L.huge_cap + 1);
     L.hoff_tmp = (uint64_t *)c.take<char>(scan_workspace_bytes<uint64_t>(L.huge_cap + 1));
     L.sort_ws = c.take<char>(sort_workspace_bytes(L.pair_cap));
+    memset(&L.pre, 0, sizeof L.pre);
+    if (p->flags & (AST_FLAG_ORDER_AUTO | AST_FLAG_ORDER_ALWAYS)) {
+        const size_t n = (size_t)(p->n > 0 ? p->n : 1);
+        L.pre.counts = c.take<unsigned long long>(2);
+        L.pre.ka = c.take<uint64_t>(n);
+        L.pre.kb = c.take<uint64_t>(n);
+        L.pre.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
+        L.pre.spos = c.take<double>(3 * n);
+        L.pre.sh = c.take<double>(n);
+        L.pre.sprop[0] = c.take<double>(n);
+        L.pre.sprop[1] = nullptr;
+    }
     L.bytes = c.bytes();
     return L;
 }
@@ -541,11 +555,30 @@ extern "C" int ast_grid3d(const ast_grid3d_params *p, const double *pos, const d
     StageTimer tm(timing, s), tk(timing, s);
     ast_project2d_stats st;
     memset(&st, 0, sizeof st);
+    tm.begin(7);
+    tk.begin(6);
+    // optional spatial pre-ordering (presort.cuh): key = brick of the particle's own position
+    if ((p->flags & (AST_FLAG_ORDER_AUTO | AST_FLAG_ORDER_ALWAYS)) && p->n > 0) {
+        OrderGrid og;
+        memset(&og, 0, sizeof og);
+        og.dims = 3;
+        const int n3[3] = { p->nx, p->ny, p->nz };
+        for (int k = 0; k < 3; ++k) {
+            og.col[k] = k;
+            og.lo[k] = p->lo[k];
+            og.inv_cell[k] = 1.0 / ((p->hi[k] - p->lo[k]) / n3[k] * BRICK);
+            og.n[k] = (n3[k] + BRICK - 1) / BRICK;
+        }
+        int done = 0, nl = 0;
+        const double *props1[1] = { prop };
+        AST_CUDA_TRY(presort_particles((p->flags & AST_FLAG_ORDER_ALWAYS) ? 2 : 1, og, pos, h, props1, 1, p->n, L.pre, s, &done, &nl));
+        st.n_launches += nl;
+        st.reordered = done;
+        if (done) { pos = L.pre.spos; h = L.pre.sh; prop = L.pre.sprop[0]; }
+    }
     P3 a = make_p3(p, pos, h, prop, out);
     a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp;
     const size_t nvox = (size_t)p->nx * p->ny * p->nz;
-    tm.begin(7);
-    tk.begin(6);
     if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * nvox, s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_pairs, 0, sizeof(uint64_t) * (L.nb + 1), s));
     AST_CUDA_TRY(cudaMemsetAsync(L.block_huge, 0, sizeof(uint64_t) * (L.nb + 1), s));

@@ -30,6 +30,7 @@
 #include "ast_math.h"
 #include "block_utils.cuh"
 #include "common.cuh"
+#include "presort.cuh"
 #include "scan_sort.cuh"
 #include "work_items.cuh"
 
@@ -937,6 +938,7 @@ struct Layout2 {
                                 // zeroed per call
     int *wexp;
     uint8_t *block_heavy;       // nb flags written by K0: the block holds particles K1 has to classify
+    PresortBuffers pre;         // only with AST_FLAG_ORDER_AUTO / _ALWAYS
     RoundSet set;
     void *sort_ws;
     size_t bytes;
@@ -993,6 +995,17 @@ static Layout2 layout2(const ast_project2d_params *p, void *ws)
     L.set.seg_off = c.take<uint32_t>(L.ntiles + 1);
     L.set.seg_tmp = c.take<uint32_t>(scan_num_blocks(L.ntiles + 1) + 2);
     L.sort_ws = c.take<char>(sort_workspace_bytes(L.win));
+    memset(&L.pre, 0, sizeof L.pre);
+    if (p->flags & (AST_FLAG_ORDER_AUTO | AST_FLAG_ORDER_ALWAYS)) {
+        const size_t n = (size_t)(p->n > 0 ? p->n : 1);
+        L.pre.counts = c.take<unsigned long long>(2);
+        L.pre.ka = c.take<uint64_t>(n);
+        L.pre.kb = c.take<uint64_t>(n);
+        L.pre.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
+        L.pre.spos = c.take<double>(3 * n);
+        L.pre.sh = c.take<double>(n);
+        for (int k = 0; k < AST_MAX_PROPS; ++k) L.pre.sprop[k] = k < p->n_prop ? c.take<double>(n) : nullptr;
+    }
     L.bytes = c.bytes();
     return L;
 }
@@ -1156,13 +1169,34 @@ extern "C" int ast_project2d(const ast_project2d_params *p, const double *pos, c
     R.s = s;
     memset(&R.st, 0, sizeof R.st);
     ast_project2d_stats &st = R.st;
+    tm.begin(7);
+    // optional spatial pre-ordering (presort.cuh): key = tile of the particle's own position (timed with the memsets, stage 6)
+    const double *sorted_prop[AST_MAX_PROPS] = { nullptr, nullptr };
+    tk.begin(6);
+    if ((p->flags & (AST_FLAG_ORDER_AUTO | AST_FLAG_ORDER_ALWAYS)) && p->n > 0) {
+        OrderGrid og;
+        memset(&og, 0, sizeof og);
+        og.dims = 2;
+        plane_columns(p->axis, og.col[0], og.col[1]);
+        const int nt[2] = { (p->nx + TILE - 1) / TILE, (p->ny + TILE - 1) / TILE };
+        const double lo2[2] = { p->x_min, p->y_min }, d2[2] = { (p->x_max - p->x_min) / p->nx, (p->y_max - p->y_min) / p->ny };
+        for (int k = 0; k < 2; ++k) { og.lo[k] = lo2[k]; og.inv_cell[k] = 1.0 / (d2[k] * TILE); og.n[k] = nt[k]; }
+        og.n[2] = 1;
+        int done = 0, nl = 0;
+        AST_CUDA_TRY(presort_particles((p->flags & AST_FLAG_ORDER_ALWAYS) ? 2 : 1, og, pos, h, prop, p->n_prop, p->n, L.pre, s, &done, &nl));
+        st.n_launches += nl;
+        st.reordered = done;
+        if (done) {
+            pos = L.pre.spos; h = L.pre.sh;
+            for (int k = 0; k < p->n_prop; ++k) sorted_prop[k] = L.pre.sprop[k];
+            prop = sorted_prop;
+        }
+    }
     R.a = make_p2(p, pos, h, prop, out);
     P2 &a = R.a;
     a.pcount = L.pcount; a.pmask = L.pmask; a.wexp = L.wexp; a.totals = L.ctrl; a.ptmask = L.ptmask; a.ptorg = L.ptorg;
     { int dev = 0; R.sm_count = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&R.sm_count, cudaDevAttrMultiProcessorCount, dev); }
 
-    tm.begin(7);
-    tk.begin(6);
     if (!(p->flags & AST_FLAG_ACCUMULATE)) AST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * a.map_stride * p->n_prop, s));
     AST_CUDA_TRY(cudaMemsetAsync(L.ctrl, 0, sizeof(unsigned long long) * 3 + sizeof(int) * AST_MAX_PROPS, s));     // totals, heavy count, exponents
     tk.end();

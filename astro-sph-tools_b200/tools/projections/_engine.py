@@ -70,6 +70,20 @@ class Projector2D:
         else:
             p.kernel_id = int(kernel)
 
+    @staticmethod
+    def _order_flags(presort):
+        """flags for the optional spatial pre-ordering (presort.cuh): 'auto' lets the library look at a sample of the input order
+        on every call (one small kernel and one stream synchronisation, ~20 us; sets below 65 536 particles are never touched),
+        'always' orders without looking, 'never' leaves the input alone.  Both paths give the same map up to the order of the
+        float additions."""
+        if presort in (None, False, "never"):
+            return 0
+        if presort in (True, "always"):
+            return _lib.FLAG_ORDER_ALWAYS
+        if presort in ("auto", "sample"):
+            return _lib.FLAG_ORDER_AUTO
+        raise ValueError("presort must be 'auto', 'always' or 'never'")
+
     def _params(self, n, image_size, axis, bounds, kernel, n_prop, periodic, box, timing, accumulate):
         p = _lib.Project2DParams()
         p.n = int(n)
@@ -109,7 +123,7 @@ class Projector2D:
 
     # ---- device-resident call -----------------------------------------------------------------------------
     def project(self, pos, h, props, image_size, axis, bounds, kernel="cubic_spline_3d", periodic=False, box=None,
-                out=None, timing=False, accumulate=False, stream=None):
+                out=None, timing=False, accumulate=False, stream=None, presort="auto"):
         """pos (N,3), h (N,), props = tensor (N,) or list of <= 2 tensors: float64 CUDA tensors.
         Returns the float64 CUDA map(s): (nx,ny) for a single tensor, (P,nx,ny) for a list."""
         torch = self.torch
@@ -122,6 +136,7 @@ class Projector2D:
             if t.dtype != torch.float64 or tuple(t.shape) != shape or not t.is_cuda or not t.is_contiguous():
                 raise ValueError("device inputs must be contiguous float64 CUDA tensors of shapes (N,3), (N,), (N,)")
         p = self._params(n, image_size, axis, bounds, kernel, len(plist), periodic, box, timing, accumulate)
+        p.flags |= self._order_flags(presort)
         if out is None:
             out = torch.empty((len(plist), p.nx, p.ny), dtype=torch.float64, device=self.device)
         elif out.dtype != torch.float64 or out.numel() != len(plist) * p.nx * p.ny or not out.is_contiguous():
@@ -135,7 +150,7 @@ class Projector2D:
             _lib.check(self.lib.ast_project2d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), prop_ptrs, _lib.ptr(out), _lib.ptr(ws),
                                               C.c_size_t(ws.numel()), _lib.stream_ptr(stream), C.byref(stats)))
         self.last_stats = dict(n_pairs=stats.n_pairs, n_huge=stats.n_huge, n_rounds=stats.n_rounds,
-                               n_launches=stats.n_launches, stage_ms=list(stats.stage_ms))
+                               n_launches=stats.n_launches, stage_ms=list(stats.stage_ms), reordered=bool(stats.reordered))
         out = out.view(len(plist), p.nx, p.ny)
         return out[0] if single else out
 

@@ -72,7 +72,7 @@ class Gridder3D:
         return self._ws
 
     def grid(self, pos, h, prop, grid_size, lo, hi, kernel="cubic_spline_3d", periodic=False, box=None, out=None, timing=False,
-             accumulate=False, stream=None):
+             accumulate=False, stream=None, presort="auto"):
         """pos (N,3), h (N,), prop (N,) float64 CUDA tensors -> (nx,ny,nz) float64 CUDA tensor"""
         torch = self.torch
         n = pos.shape[0]
@@ -80,6 +80,14 @@ class Gridder3D:
             if t.dtype != torch.float64 or tuple(t.shape) != shape or not t.is_cuda or not t.is_contiguous():
                 raise ValueError("device inputs must be contiguous float64 CUDA tensors of shapes (N,3), (N,), (N,)")
         p = self.params(n, grid_size, lo, hi, kernel, periodic, box, timing, accumulate)
+        # optional spatial pre-ordering: 'auto' = the library looks at a sample of the input order (the deposition is 27 % faster
+        # on the randomly ordered NFW set of config 4 when the particles are first ordered by brick), 'always', 'never'
+        if presort in (True, "always"):
+            p.flags |= _lib.FLAG_ORDER_ALWAYS
+        elif presort in ("auto", "sample"):
+            p.flags |= _lib.FLAG_ORDER_AUTO
+        elif presort not in (None, False, "never"):
+            raise ValueError("presort must be 'auto', 'always' or 'never'")
         if out is None:
             out = torch.empty((p.nx, p.ny, p.nz), dtype=torch.float64, device=self.device)
         stats = _lib.Project2DStats()
@@ -90,7 +98,7 @@ class Gridder3D:
             _lib.check(self.lib.ast_grid3d(C.byref(p), _lib.ptr(pos), _lib.ptr(h), _lib.ptr(prop), _lib.ptr(out), _lib.ptr(ws),
                                            C.c_size_t(ws.numel()), _lib.stream_ptr(stream), C.byref(stats)))
         self.last_stats = dict(n_pairs=stats.n_pairs, n_huge=stats.n_huge, n_rounds=stats.n_rounds,
-                               n_launches=stats.n_launches, stage_ms=list(stats.stage_ms))
+                               n_launches=stats.n_launches, stage_ms=list(stats.stage_ms), reordered=bool(stats.reordered))
         return out
 
 

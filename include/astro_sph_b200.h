@@ -58,7 +58,11 @@ typedef enum ast_kernel {
 enum {
     AST_FLAG_PERIODIC = 1,       /* deposit the 9 (2-D) / 27 (3-D) periodic images, shifts ia*box_a etc. */
     AST_FLAG_ACCUMULATE = 2,     /* add to `out` instead of zeroing it first */
-    AST_FLAG_TIMING = 4          /* record CUDA events around every stage and return stage_ms (synchronises) */
+    AST_FLAG_TIMING = 4,         /* record CUDA events around every stage and return stage_ms (synchronises) */
+    AST_FLAG_ORDER_AUTO = 8,     /* look at a sample of consecutive particles; if they are far apart in space (an incoherent input
+                                    order) sort the particles by the tile / brick of their own position first and run on the copy
+                                    (one more stream synchronisation, workspace grows by ~64 bytes per particle) */
+    AST_FLAG_ORDER_ALWAYS = 16   /* pre-order without looking */
 };
 
 /* ---- 2-D line-of-sight projection ------------------------------------------------------------------
@@ -92,8 +96,10 @@ typedef struct ast_project2d_stats {
     int64_t n_huge;              /* particle-images on the large-h list */
     int64_t n_rounds;            /* passes over the pair window (1 unless pair_capacity < n_pairs or huge_capacity < n_huge) */
     int64_t n_launches;          /* kernels launched by this call */
-    float stage_ms[8];           /* AST_FLAG_TIMING: 0 bin+direct deposit, 1 scan, 2 emit, 3 sort, 4 tile ranges,
-                                    5 tile accumulate, 6 memset, 7 total */
+    float stage_ms[8];           /* AST_FLAG_TIMING: 0 bin+direct deposit, 1 scan, 2 emit, 3 sort, 4 tile ranges / pair records,
+                                    5 tile accumulate, 6 pre-ordering + memset, 7 total */
+    int32_t reordered;           /* 1: the particles were pre-ordered (AST_FLAG_ORDER_AUTO found the input incoherent, or _ALWAYS) */
+    int32_t reserved;
 } ast_project2d_stats;
 
 int ast_project2d_workspace_bytes(const ast_project2d_params *p, size_t *bytes /* host */);

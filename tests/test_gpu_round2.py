@@ -133,3 +133,42 @@ def test_rounds_over_a_small_pair_window_equal_one_round():
     torch.cuda.synchronize()
     assert one.last_stats["n_rounds"] == 1 and many.last_stats["n_rounds"] >= 7 and one.last_stats["n_pairs"] == many.last_stats["n_pairs"]
     assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
+
+
+def test_spatial_pre_ordering_gives_the_same_map(oracle):
+    """a randomly ordered set: AST_FLAG_ORDER_AUTO detects it from a sample and projects a copy ordered by tile; lattice order
+    is left alone; 'always' / 'never' are honoured; the map is the oracle's either way (only the order of additions changes)"""
+    import torch
+    from astro_sph_tools_b200 import synthetic
+    from astro_sph_tools_b200.tools.projections import Projector2D, Gridder3D
+    s = synthetic.s1(48, k=48, h_mode="uniform")
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(s["h"]))
+    h = s["h"] * rng.uniform(0.05, 1.5, len(s["h"]))
+    props = [s["mass"], s["mass"] * rng.uniform(1, 100, len(h))]
+    ref = oracle.project2d(s["pos"], h, np.stack(props), (384, 384), 2, 0.0, 1.0, 0.0, 1.0)
+    eng = Projector2D()
+    args = ((384, 384), 2, (0.0, 1.0, 0.0, 1.0))
+    lat = eng.project(dev(s["pos"]), dev(h), [dev(q) for q in props], *args).cpu().numpy()
+    assert eng.last_stats["reordered"] is False
+    rnd_in = (dev(s["pos"][perm]), dev(h[perm]), [dev(q[perm]) for q in props])
+    rnd = eng.project(*rnd_in, *args).cpu().numpy()
+    assert eng.last_stats["reordered"] is True
+    again = eng.project(*rnd_in, *args).cpu().numpy()
+    assert eng.last_stats["reordered"] is True
+    never = eng.project(*rnd_in, *args, presort="never").cpu().numpy()
+    assert eng.last_stats["reordered"] is False
+    always = eng.project(dev(s["pos"]), dev(h), [dev(q) for q in props], *args, presort="always").cpu().numpy()
+    assert eng.last_stats["reordered"] is True
+    for m in (lat, rnd, again, never, always):
+        for k in range(2):
+            check(m[k], ref[k])
+    # 3-D
+    g = Gridder3D()
+    ref3 = oracle.grid3d(s["pos"], h, s["mass"], (40, 40, 40), (0, 0, 0), (1, 1, 1), periodic=True, box=(1.0, 1.0, 1.0))
+    a3 = g.grid(dev(s["pos"][perm]), dev(h[perm]), dev(s["mass"][perm]), (40, 40, 40), (0, 0, 0), (1, 1, 1), periodic=True, box=1.0).cpu().numpy()
+    assert g.last_stats["reordered"] is True
+    b3 = g.grid(dev(s["pos"]), dev(h), dev(s["mass"]), (40, 40, 40), (0, 0, 0), (1, 1, 1), periodic=True, box=1.0).cpu().numpy()
+    assert g.last_stats["reordered"] is False
+    for m in (a3, b3):
+        assert rel_l2(m, ref3) <= 1e-5 and abs(m.sum() - ref3.sum()) <= 1e-6 * np.abs(ref3).sum()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from astro_sph_tools_b200 import _lib
     assert C.sizeof(_lib.Project2DParams) == 8 + 6 * 4 + 6 * 8 + 4 * 8 + 8 + 2 * 4
-    assert C.sizeof(_lib.Project2DStats) == 4 * 8 + 8 * 4
+    assert C.sizeof(_lib.Project2DStats) == 4 * 8 + 8 * 4 + 2 * 4         # ... stage_ms[8], reordered, reserved
 
 
 def test_c_abi_argument_validation_without_gpu():
