@@ -518,6 +518,19 @@ __global__ void __launch_bounds__(128) knn_lockstep_kernel(KnnArgs a)
     }
 }
 
+}  // namespace ast
+#include "knn_select.cuh"
+namespace ast {
+
+// failed queries of the selection kernel -> ordered list of cell-ordered positions (flags already scanned exclusively)
+__global__ void knn_fail_compact_kernel(const uint32_t *__restrict__ excl, int64_t n, const uint32_t *__restrict__ total, uint32_t *__restrict__ qlist)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t e = excl[s], nx = s + 1 < n ? excl[s + 1] : *total;
+    if (nx != e) qlist[e] = (uint32_t)s;
+}
+
 struct KnnLayout {
     int G;
     int64_t ncell, nq;
@@ -635,6 +648,62 @@ static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout
     return AST_OK;
 }
 
+// ---- selection fast path (h only) --------------------------------------------------------------------------------------
+static bool select_usable(const ast_knn_params *p, const KnnLayout &L, bool want_lists, int64_t n_build)
+{
+    static const bool enabled = env_flag("AST_KNN_SELECT", true);
+    if (!enabled || want_lists || (p->flags & (AST_KNN_DIVERGING | AST_KNN_NO_SELECT))) return false;
+    if (L.G < 2 * (kSelBS + 2 * kSelR) || n_build < 4096) return false;        // wrapped region pieces must stay disjoint / minimum image
+    if (!(p->box > 0.0)) {
+        double lo = INFINITY, hi = 0.0;
+        for (int c = 0; c < 3; ++c) { const double e = p->hi[c] - p->lo[c]; if (!(e > 0.0)) return false; lo = e < lo ? e : lo; hi = e > hi ? e : hi; }
+        if (hi > 1.5 * lo) return false;                                           // the float32 error bound assumes near-cubic cells
+    }
+    return true;
+}
+
+// runs the selection kernel for every query; *need_lockstep = some queries were flagged (a.qlist / a.nq then describe them)
+static int launch_select(const ast_knn_params *p, const KnnLayout &L, KnnArgs &a, int64_t n_build, cudaStream_t s, bool *need_lockstep)
+{
+    SelParams sp;
+    double cs_min = a.g.cs[0] < a.g.cs[1] ? a.g.cs[0] : a.g.cs[1];
+    cs_min = cs_min < a.g.cs[2] ? cs_min : a.g.cs[2];
+    const double dref = ((double)kSelR + 0.5) * cs_min;
+    for (int c = 0; c < 3; ++c) sp.sc[c] = a.g.cs[c] / dref;
+    sp.dref2 = dref * dref;
+    // a sphere of R cells holds 4.19 R^3 / W^3 of the region's particles when they are spread evenly: demand 0.9 K of them;
+    // a region that does not fit the staging buffer is so dense that the ring traversal (27 cells, not 512) is the cheaper search
+    const double wreg = (double)(kSelBS + 2 * kSelR);
+    sp.m_min = (uint32_t)(0.9 * (double)p->k * wreg * wreg * wreg / (4.19 * kSelR * kSelR * kSelR));
+    sp.m_max = kSelChunk;
+    sp.fail = L.qflag;
+    const int nbk = (L.G + kSelBS - 1) / kSelBS;
+    const unsigned nblocks = (unsigned)nbk * nbk * nbk;
+    const size_t smem = sizeof(SelShared);
+    static bool attr_set = false;
+    if (!attr_set) {
+        AST_CUDA_TRY(cudaFuncSetAttribute(knn_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AST_CUDA_TRY(cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (a.g.box > 0.0) knn_select_kernel<true><<<nblocks, kSelThreads, smem, s>>>(a, sp);
+    else knn_select_kernel<false><<<nblocks, kSelThreads, smem, s>>>(a, sp);
+    AST_KERNEL_CHECK(s, "knn_select_kernel");
+    uint32_t n_fail = 0;
+    uint32_t *total = reinterpret_cast<uint32_t *>(L.counter + 2);
+    AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n_build, L.scan_tmp, total, s));
+    AST_CUDA_TRY(cudaMemcpyAsync(&n_fail, total, sizeof n_fail, cudaMemcpyDeviceToHost, s));
+    AST_CUDA_TRY(cudaStreamSynchronize(s));
+    *need_lockstep = n_fail > 0;
+    if (n_fail) {
+        knn_fail_compact_kernel<<<(unsigned)((n_build + 255) / 256), 256, 0, s>>>(L.qflag, n_build, total, L.qlist);
+        a.qlist = L.qlist;
+        a.nq = (int64_t)n_fail;
+    }
+    if (getenv("AST_KNN_VERBOSE")) fprintf(stderr, "[ast_knn_h] selection kernel: %u of %lld queries left to the lock-step kernel\n", n_fail, (long long)a.nq);
+    return AST_OK;
+}
+
 }  // namespace ast
 
 using namespace ast;
@@ -733,7 +802,9 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
             }
         }
         KnnArgs a;
-        rc = knn_build(p, pos, L, subset, q_begin, q_end, s, a, limited ? n_build : -1, limited ? L.kept : nullptr);
+        const int64_t n_fast = limited ? n_build : n;
+        const bool fast = select_usable(p, L, want, n_fast);
+        rc = knn_build(p, pos, L, subset && !fast, q_begin, q_end, s, a, limited ? n_build : -1, limited ? L.kept : nullptr);
         if (rc) return rc;
         a.nq = nq;
         a.q_begin = q_begin;
@@ -744,10 +815,18 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
             else if (p->k <= 64) launch_query<64>(a, want, s);
             else launch_query<128>(a, want, s);
         } else {
-            if (p->k <= 32) launch_lockstep<32>(a, want, s);
-            else if (p->k <= 48) launch_lockstep<48>(a, want, s);
-            else if (p->k <= 64) launch_lockstep<64>(a, want, s);
-            else launch_lockstep<128>(a, want, s);
+            bool run_lockstep = true;
+            if (fast) {
+                // selection kernel over blocks of cells (knn_select.cuh); what it cannot verify goes to the lock-step kernel
+                rc = launch_select(p, L, a, n_fast, s, &run_lockstep);
+                if (rc) return rc;
+            }
+            if (run_lockstep) {
+                if (p->k <= 32) launch_lockstep<32>(a, want, s);
+                else if (p->k <= 48) launch_lockstep<48>(a, want, s);
+                else if (p->k <= 64) launch_lockstep<64>(a, want, s);
+                else launch_lockstep<128>(a, want, s);
+            }
         }
         AST_CUDA_TRY(cudaGetLastError());
         if (!limited) break;

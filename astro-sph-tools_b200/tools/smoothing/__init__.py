@@ -31,7 +31,7 @@ class SmoothingLengthSolver:
         self._lock = threading.RLock()        # one workspace: calls on this solver serialise
 
     def solve(self, pos, k=DEFAULT_K, box_size=None, q_begin=0, q_count=0, want_neighbours=False, want_distances=False,
-              stream=None, kernel="lockstep", full_build=False, cell_target=None):
+              stream=None, kernel="select", full_build=False, cell_target=None):
         """pos: (N,3) float64 CUDA tensor.  Returns h (Q,) [, idx (Q,k) int32] [, dist (Q,k)] as CUDA tensors where
         Q = q_count or N.  Multi-GPU use: every rank passes all positions and its own [q_begin, q_begin+q_count)."""
         torch = self.torch
@@ -39,7 +39,7 @@ class SmoothingLengthSolver:
             raise ValueError("pos must be a contiguous float64 CUDA tensor of shape (N, 3)")
         n = pos.shape[0]
         p = _lib.KnnParams()
-        p.n = n; p.k = int(k); p.flags = {"lockstep": 0, "diverging": 1}[kernel] | (4 if full_build else 0)      # AST_KNN_* query-kernel selection (csrc/knn.cu)
+        p.n = n; p.k = int(k); p.flags = {"select": 0, "lockstep": 8, "diverging": 1}[kernel] | (4 if full_build else 0)      # AST_KNN_* query-kernel selection (csrc/knn.cu): select = selection over blocks of cells + lock-step for what it cannot verify (h only; neighbour lists always take the lock-step kernel)
         p.box = float(box_size) if box_size else 0.0
         if p.box <= 0.0 and n > 0:
             lo = pos.min(dim=0).values.cpu(); hi = pos.max(dim=0).values.cpu()

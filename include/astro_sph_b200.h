@@ -185,7 +185,7 @@ int ast_bin3d(const ast_grid3d_params *p, const double *pos, const double *h, in
  *   box) -- the cell grid is built over that extent. */
 /* flags: AST_KNN_DIVERGING selects the first query kernel (every thread walks its traversal on its own) instead of the
  * default, in which the 32 queries of a warp walk their traversals in lock step (tuning / tests). */
-enum { AST_KNN_DIVERGING = 1, AST_KNN_FULL_BUILD = 4 };   /* AST_KNN_FULL_BUILD: with a query subset, build the cell list from ALL
+enum { AST_KNN_DIVERGING = 1, AST_KNN_FULL_BUILD = 4, AST_KNN_NO_SELECT = 8 };   /* AST_KNN_FULL_BUILD: with a query subset, build the cell list from ALL
                                                               particles instead of those within reach of the queries */
 typedef struct ast_knn_params {
     int64_t n;

@@ -107,12 +107,13 @@ def test_nearest_halo_lookup_separate_query_set(oracle):
 @pytest.mark.parametrize("n,k,box,ct", [(30000, 48, 1.0, 0.0), (30000, 48, None, 0.0), (2000, 8, 1.0, 60.0), (700, 16, 1.0, 90.0),
                                          (900, 4, 1.0, 0.5), (5000, 48, 3.0, 8.0), (64, 8, 1.0, 0.0)])
 def test_all_query_kernels_agree_with_scipy(oracle, n, k, box, ct):
-    """both query kernels (lock-step thread per query = default, diverging thread per query); small grids (G = 2..6) take
+    """all query kernels (selection over blocks of cells + lock-step remainder = default, lock-step thread per query alone,
+    diverging thread per query); small grids (G = 2..6) take
     the per-pair wrap path, large ones the constant-shift path"""
     rng = np.random.default_rng(n * 7 + k)
     pos = rng.uniform(0, box or 1.0, (n, 3))
     ref = oracle.knn_scipy(pos, k, box, workers=-1)[0]
-    for kernel in ("lockstep", "diverging"):
+    for kernel in ("select", "lockstep", "diverging"):
         assert np.array_equal(gpu_knn(pos, k, box, cell_target=ct, kernel=kernel), ref), kernel
 
 
@@ -168,3 +169,31 @@ def test_reach_limited_build_for_query_subsets(oracle, box):
     for lo, hi in ((0, 3000), (12000, 15000), (len(cl) - 2500, len(cl))):
         h, idx, dist = gpu_knn(cl, 48, box, lists=True, q_begin=lo, q_count=hi - lo)
         assert np.array_equal(h, ref[0][lo:hi]) and np.array_equal(dist, ref[1][lo:hi]), (lo, hi)
+
+
+@pytest.mark.parametrize("kind,n,k,box", [("s1", 40, 48, 1.0), ("s1", 33, 48, None), ("uniform", 60000, 48, 1.0), ("uniform", 50000, 32, None),
+                                          ("uniform", 50000, 100, 1.0), ("s2", 60000, 48, 1.0), ("s2", 60000, 16, None),
+                                          ("aniso", 50000, 48, None), ("dup", 40000, 48, 1.0)])
+def test_selection_kernel_bit_equal_to_scipy(oracle, kind, n, k, box):
+    """the selection kernel (float32 histogram + exact float64 edge band, knn_select.cuh) with its lock-step remainder against
+    scipy on jittered lattices, uniform, clustered (most queries fall back), anisotropic extents (1.4 : 1 : 1, still on the
+    fast path), and a set with exactly duplicated points (tied distances across the K-th)"""
+    from astro_sph_tools_b200 import synthetic
+    rng = np.random.default_rng(n + k)
+    if kind == "s1":
+        pos, _ = synthetic.s1_positions(n)
+    elif kind == "s2":
+        pos, _ = synthetic.s2_positions(n, 1.0, n_haloes=6, seed=3)
+    else:
+        pos = rng.uniform(0, 1.0, (n, 3))
+    if kind == "aniso":
+        pos = pos * np.array([1.4, 1.0, 1.0])
+    if kind == "dup":
+        pos[n // 2:] = pos[:n - n // 2]                            # every point twice: distances tie pairwise
+    if box is None and kind in ("s1", "s2"):
+        pos = pos * 2.0 - 7.0
+    ref = oracle.knn_scipy(pos, k, box, workers=-1)[0]
+    got = gpu_knn(pos, k, box, kernel="select")
+    assert np.array_equal(got, ref)
+    lo, cnt = len(pos) // 3, len(pos) // 4                          # a query slice through the fast path
+    assert np.array_equal(gpu_knn(pos, k, box, kernel="select", q_begin=lo, q_count=cnt, full_build=True), ref[lo:lo + cnt])
