@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(KnnArgs a, SelP
             for (int r = 0; r < 6; ++r) {                        // (rolled: the unrolled kernel stalled on instruction fetch, ncu no_inst 27 %)
                 int i = (int)S.seg_off[run0 + 2 * kSelW * r];
                 const int end = (int)S.seg_off[run0 + 2 * kSelW * r + 12];
-                for (; i + 4 <= end; i += 4) {                   // four loads in flight before the first atomic (which orders them)
-                    const float4 c0 = S.cand[i], c1 = S.cand[i + 1], c2 = S.cand[i + 2], c3 = S.cand[i + 3];
+                for (; i + 4 <= end; i += 4) {                   // four loads in flight before the first atomic (which orders them);
+                    const float4 c0 = S.cand[i], c1 = S.cand[i + 1], c2 = S.cand[i + 2], c3 = S.cand[i + 3];      // eight: 79 registers, 2 % slower
                     deposit(c0); deposit(c1); deposit(c2); deposit(c3);
                 }
                 for (; i < end; ++i) deposit(S.cand[i]);

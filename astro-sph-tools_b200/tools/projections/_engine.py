@@ -123,9 +123,12 @@ class Projector2D:
 
     # ---- device-resident call -----------------------------------------------------------------------------
     def project(self, pos, h, props, image_size, axis, bounds, kernel="cubic_spline_3d", periodic=False, box=None,
-                out=None, timing=False, accumulate=False, stream=None, presort="auto"):
+                out=None, timing=False, accumulate=False, stream=None, presort="never"):
         """pos (N,3), h (N,), props = tensor (N,) or list of <= 2 tensors: float64 CUDA tensors.
-        Returns the float64 CUDA map(s): (nx,ny) for a single tensor, (P,nx,ny) for a list."""
+        Returns the float64 CUDA map(s): (nx,ny) for a single tensor, (P,nx,ny) for a list.
+        presort: 'never' (default for device-resident data: the caller knows its order, and the look costs one stream
+        synchronisation, 0.06 ms -- 4 % of the step when every support is below a pixel), 'auto' (look at a sample of the
+        input order and project a tile-ordered copy if it is incoherent; what the host paths use), 'always'."""
         torch = self.torch
         single = not isinstance(props, (list, tuple))
         plist = [props] if single else list(props)
@@ -175,7 +178,7 @@ class Projector2D:
                 pos_d, h_d = to_dev(positions), to_dev(smoothing_lengths)      # uploads ordered on the stream that computes
                 props_d = [to_dev(q) for q in plist]
             out = self.project(pos_d, h_d, props_d[0] if single else props_d, image_size, axis, bounds, kernel, periodic, box,
-                               stream=stream)
+                               stream=stream, presort="auto")
         else:
             positions = np.ascontiguousarray(positions)
             smoothing_lengths = np.ascontiguousarray(smoothing_lengths)
@@ -222,7 +225,7 @@ class Projector2D:
                         ready[k].record(copy)
                     compute.wait_event(ready[k])
                     self.project(st["pos"][:m], st["h"][:m], [q[:m] for q in st["props"]], image_size, axis, bounds, kernel,
-                                 periodic, box, out=out, accumulate=b > 0, stream=compute)
+                                 periodic, box, out=out, accumulate=b > 0, stream=compute, presort="auto")
                     n_launch += self.last_stats["n_launches"]
                     free[k].record(compute)
                 self.last_stats["n_launches"] = n_launch

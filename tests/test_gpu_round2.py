@@ -149,13 +149,13 @@ def test_spatial_pre_ordering_gives_the_same_map(oracle):
     ref = oracle.project2d(s["pos"], h, np.stack(props), (384, 384), 2, 0.0, 1.0, 0.0, 1.0)
     eng = Projector2D()
     args = ((384, 384), 2, (0.0, 1.0, 0.0, 1.0))
-    lat = eng.project(dev(s["pos"]), dev(h), [dev(q) for q in props], *args).cpu().numpy()
+    lat = eng.project(dev(s["pos"]), dev(h), [dev(q) for q in props], *args, presort="auto").cpu().numpy()
     assert eng.last_stats["reordered"] is False
     rnd_in = (dev(s["pos"][perm]), dev(h[perm]), [dev(q[perm]) for q in props])
-    rnd = eng.project(*rnd_in, *args).cpu().numpy()
+    rnd = eng.project(*rnd_in, *args, presort="auto").cpu().numpy()
     assert eng.last_stats["reordered"] is True
-    again = eng.project(*rnd_in, *args).cpu().numpy()
-    assert eng.last_stats["reordered"] is True
+    again = eng.project(*rnd_in, *args).cpu().numpy()                      # device-resident default: 'never'
+    assert eng.last_stats["reordered"] is False
     never = eng.project(*rnd_in, *args, presort="never").cpu().numpy()
     assert eng.last_stats["reordered"] is False
     always = eng.project(dev(s["pos"]), dev(h), [dev(q) for q in props], *args, presort="always").cpu().numpy()
