@@ -282,7 +282,7 @@ def sub_c5(ctx, args, pos_all_d, peak):
            "ms": ms, "queries_per_s": N / (ms * 1e-3), "n_gpus": ctx.world,
            "roofline": {"bound": "hbm", "achieved": N * 32 / (ms * 1e-3) / 1e9, "peak": peak * ctx.world, "unit": "GB/s",
                         "frac": N * 32 / (ms * 1e-3) / 1e9 / (peak * ctx.world), "algorithmic_bytes": N * 32,
-                        "note": "N*(24+8) bytes; ~250 float64 candidate distances per query make it FP64/selection-bound"}}
+                        "note": "N*(24+8) bytes; the selection kernel evaluates ~585 float32 candidate distances per query twice (histogram pass, band pass): FP32-issue / shared-memory bound, DRAM traffic ~= the input (profiles/r02_v13_ncu_knn_select.txt)"}}
     if ctx.world > 1:
         # the same search WITHOUT replicating the positions: slabs of equal count along x + ghost zones, one all-to-all of
         # positions and one of results (distributed.smoothing_lengths_slabs); must give the very same bits

@@ -183,10 +183,13 @@ int ast_bin3d(const ast_grid3d_params *p, const double *pos, const double *h, in
  *   positions must satisfy 0 <= x < box.  idx_out (nullable): N*k int32 neighbour indices, ascending
  *   (distance, index).  dist_out (nullable): N*k float64.  Positions must lie in [lo, hi] per axis (open
  *   box) -- the cell grid is built over that extent. */
-/* flags: AST_KNN_DIVERGING selects the first query kernel (every thread walks its traversal on its own) instead of the
- * default, in which the 32 queries of a warp walk their traversals in lock step (tuning / tests). */
-enum { AST_KNN_DIVERGING = 1, AST_KNN_FULL_BUILD = 4, AST_KNN_NO_SELECT = 8 };   /* AST_KNN_FULL_BUILD: with a query subset, build the cell list from ALL
-                                                              particles instead of those within reach of the queries */
+/* flags: by default the h-only call (idx_out == dist_out == NULL) runs the selection kernel (csrc/knn_select.cuh: CTA per block
+ * of cells, float32 histogram + exact float64 band) and hands the queries it cannot verify to the lock-step kernel, in which
+ * the 32 queries of a warp walk their ring traversals together; calls that want neighbour lists take the lock-step kernel.
+ * AST_KNN_NO_SELECT: lock-step kernel alone.  AST_KNN_DIVERGING: the first query kernel (every thread walks its traversal on
+ * its own).  All give the same bits (tuning / tests).  AST_KNN_FULL_BUILD: with a query subset, build the cell list from ALL
+ * particles instead of those within reach of the queries. */
+enum { AST_KNN_DIVERGING = 1, AST_KNN_FULL_BUILD = 4, AST_KNN_NO_SELECT = 8 };
 typedef struct ast_knn_params {
     int64_t n;
     int32_t k;
