@@ -58,6 +58,14 @@ class TableParams(C.Structure):
                 ("fixed_value", C.c_double)]
 
 
+ROUTE_MAX_WORLD = 32
+
+
+class SlabRouteParams(C.Structure):
+    _fields_ = [("n", C.c_int64), ("world", C.c_int32), ("periodic", C.c_int32), ("covers_all", C.c_int32), ("reserved", C.c_int32),
+                ("length", C.c_double), ("w", C.c_double), ("bounds", C.c_double * (ROUTE_MAX_WORLD + 1))]
+
+
 class WorkspaceError(RuntimeError):
     """AST_EWORKSPACE: a capacity or the workspace was too small (message says what is needed)."""
 
@@ -68,6 +76,7 @@ _lib = None
 EXPORTS = ["ast_project2d_workspace_bytes", "ast_project2d", "ast_bin2d", "ast_contrib_count2d", "ast_kernel_eval",
            "ast_sort_workspace_bytes", "ast_radix_sort_u64", "ast_grid3d_workspace_bytes", "ast_grid3d", "ast_bin3d",
            "ast_knn_workspace_bytes", "ast_knn_h", "ast_knn_query", "ast_match_ids_workspace_bytes", "ast_match_ids", "ast_gather_rows", "ast_table_interp",
+           "ast_slab_route_workspace_bytes", "ast_slab_route_count", "ast_slab_route_write",
            "ast_last_error", "ast_abi_version", "ast_tile_size",
            "ast_device_sm_count"]
 

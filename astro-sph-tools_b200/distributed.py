@@ -194,6 +194,65 @@ def _slab_plan(x, lo, length, world, n_bins=4096, group=None):
     return owner, lo + length * full.to(torch.float64) / n_bins
 
 
+def _route_torch(pos_local, x, owner, b_lo, b_hi, w, length, periodic, covers_all, world):
+    """destinations of every local particle, one pass of torch index operations per destination rank (CPU tensors: the gloo
+    tests of the host logic; also the definition the packing kernel is tested against).
+    Returns (send rows [owned -> 0 | owned -> 1 | ... | ghosts -> 0 | ...] (S,3), src_index (S,), counts (2, world) int64 on the host)."""
+    import torch
+    own_idx, ghost_idx = [], []
+    for g in range(world):
+        own = owner == g
+        if periodic:
+            t = torch.remainder(x - b_lo[g], length)
+            seg = b_hi[g] - b_lo[g]
+            d = torch.where(t <= seg, torch.zeros_like(t), torch.minimum(t - seg, length - t))
+        else:
+            d = torch.clamp(torch.maximum(b_lo[g] - x, x - b_hi[g]), min=0.0)
+        ghost = (~own) & ((d <= w) | covers_all)
+        own_idx.append(torch.nonzero(own).flatten())
+        ghost_idx.append(torch.nonzero(ghost).flatten())
+    counts = torch.tensor([[t.numel() for t in own_idx], [t.numel() for t in ghost_idx]], dtype=torch.int64)
+    src = torch.cat(own_idx + ghost_idx)
+    return pos_local[src].contiguous(), src, counts
+
+
+class _SlabRouter:
+    """the packing kernel behind ast_slab_route_count / _write (csrc/slabroute.cu): two passes over the local particles in all"""
+
+    def __init__(self, device):
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.device = device
+        self._ws = None
+
+    def route(self, pos_local, owner, bounds, w, length, periodic, covers_all, world):
+        import ctypes as C
+        import torch
+        _lib = self._lib
+        p = _lib.SlabRouteParams()
+        p.n = pos_local.shape[0]; p.world = world; p.periodic = 1 if periodic else 0; p.covers_all = 1 if covers_all else 0
+        p.length = float(length); p.w = float(w)
+        for g, b in enumerate(bounds.tolist()):
+            p.bounds[g] = b
+        need = C.c_size_t(0)
+        _lib.check(self.lib.ast_slab_route_workspace_bytes(C.byref(p), C.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = None
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        stream = _lib.stream_ptr(None)
+        counts_d = torch.empty(2 * world, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.ast_slab_route_count(C.byref(p), _lib.ptr(pos_local), _lib.ptr(owner), _lib.ptr(counts_d), _lib.ptr(self._ws),
+                                                 C.c_size_t(self._ws.numel()), stream))
+        counts = counts_d.cpu().view(2, world)
+        total = int(counts.sum())
+        send = torch.empty((total, 3), dtype=torch.float64, device=self.device)
+        src = torch.empty(total, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.ast_slab_route_write(C.byref(p), _lib.ptr(pos_local), _lib.ptr(owner), _lib.ptr(send), _lib.ptr(src),
+                                                 _lib.ptr(self._ws), C.c_size_t(self._ws.numel()), stream))
+        return send, src, counts
+
+
 def smoothing_lengths_slabs(pos_local, k=32, box_size=None, group=None, solver=None, ghost_width=None, return_stats=False):
     """Multi-GPU smoothing lengths WITHOUT replicating the positions: every rank passes the particles it holds (any index
     range, any spatial distribution: the reference's per-rank read, io/EAGLE/_SnapshotEAGLE.py:120-130) and gets their h back.
@@ -242,38 +301,34 @@ def smoothing_lengths_slabs(pos_local, k=32, box_size=None, group=None, solver=N
     b_lo, b_hi = bounds[:-1], bounds[1:]
     r_k = (3.0 * k * volume / (4.0 * np.pi * max(n_tot, 1))) ** (1.0 / 3.0)
     w = float(ghost_width) if ghost_width else 1.5 * r_k
+    router = None
+    if pos_local.is_cuda and world <= 32 and pos_local.dtype == torch.float64 and pos_local.is_contiguous():
+        router = _SlabRouter(dev)                                 # (CPU tensors -- the gloo tests of this logic -- take the torch route)
     iterations = 0
     while True:
         iterations += 1
         covers_all = bool(box_size) and w >= 0.5 * length
-        # ---- step 2: destinations.  dist_g = distance from x to slab g's interval (along the circle when periodic)
-        send_idx, send_owned = [], []
-        for g in range(world):
-            own = owner == g
-            if box_size:
-                t = torch.remainder(x - b_lo[g], length)
-                seg = b_hi[g] - b_lo[g]
-                d = torch.where(t <= seg, torch.zeros_like(t), torch.minimum(t - seg, length - t))
-            else:
-                d = torch.clamp(torch.maximum(b_lo[g] - x, x - b_hi[g]), min=0.0)
-            ghost = (~own) & ((d <= w) | covers_all)
-            io, ig = torch.nonzero(own).flatten(), torch.nonzero(ghost).flatten()
-            send_idx.append(torch.cat([io, ig]))                                 # owned first, then ghosts
-            send_owned.append(io.numel())
-        counts = torch.tensor([[t.numel() for t in send_idx], send_owned], dtype=torch.int64, device=dev)      # (2, world)
-        recv_counts = torch.empty_like(counts)
+        # ---- step 2: destinations (distance from x to slab g's interval, along the circle when periodic) and the send buffer
+        # [owned -> 0 | owned -> 1 | ... | ghosts -> 0 | ghosts -> 1 | ...]: the packing kernel on the GPU, torch index ops on the CPU
+        if router is not None:
+            send, src, counts = router.route(pos_local, owner, bounds, w, length, bool(box_size), covers_all, world)
+        else:
+            send, src, counts = _route_torch(pos_local, x, owner, b_lo, b_hi, w, length, bool(box_size), covers_all, world)
+        counts_d = counts.to(dev)
+        recv_counts = torch.empty_like(counts_d)
         for row in range(2):
-            dist.all_to_all_single(recv_counts[row], counts[row].contiguous(), group=group)
-        in_split = counts[0].tolist(); out_split = recv_counts[0].tolist(); own_from = recv_counts[1].tolist()
-        order = torch.cat(send_idx)
-        recv = torch.empty((sum(out_split), 3), dtype=pos_local.dtype, device=dev)
-        dist.all_to_all_single(recv, pos_local[order].contiguous(), output_split_sizes=out_split, input_split_sizes=in_split, group=group)
-        # ---- step 3: owned particles (in arrival order, source by source) first, then the ghosts
-        starts = np.concatenate([[0], np.cumsum(out_split)])
-        owned_rows = torch.cat([torch.arange(starts[s], starts[s] + own_from[s], device=dev) for s in range(world)])
-        ghost_rows = torch.cat([torch.arange(starts[s] + own_from[s], starts[s + 1], device=dev) for s in range(world)])
-        n_owned = owned_rows.numel()
-        pos_slab = recv[torch.cat([owned_rows, ghost_rows])].contiguous()
+            dist.all_to_all_single(recv_counts[row], counts_d[row].contiguous(), group=group)
+        send_owned, send_ghost = counts[0].tolist(), counts[1].tolist()
+        rc = recv_counts.cpu()
+        own_from, ghost_from = rc[0].tolist(), rc[1].tolist()
+        n_owned, n_ghost = sum(own_from), sum(ghost_from)
+        n_send_owned = sum(send_owned)
+        # two exchanges (owned rows, then ghost rows) leave [owned from all ranks | ghosts from all ranks]: no reorder
+        pos_slab = torch.empty((n_owned + n_ghost, 3), dtype=pos_local.dtype, device=dev)
+        dist.all_to_all_single(pos_slab[:n_owned], send[:n_send_owned], output_split_sizes=own_from, input_split_sizes=send_owned, group=group)
+        dist.all_to_all_single(pos_slab[n_owned:], send[n_send_owned:], output_split_sizes=ghost_from, input_split_sizes=send_ghost, group=group)
+        src_owned = src[:n_send_owned]
+        del send
         if n_owned:
             # the slab + ghosts fill only a fraction of the box the cell grid spans: size the cells for ~2 particles per OCCUPIED
             # cell (with the default, 8 slabs would put 14 particles in every occupied cell and 2000 candidates in front of a query)
@@ -302,7 +357,7 @@ def smoothing_lengths_slabs(pos_local, k=32, box_size=None, group=None, solver=N
     back = torch.empty(sum(send_owned), dtype=pos_local.dtype, device=dev)
     dist.all_to_all_single(back, h_owned.contiguous(), output_split_sizes=send_owned, input_split_sizes=own_from, group=group)
     h_local = torch.empty(n_loc, dtype=pos_local.dtype, device=dev)
-    h_local[torch.cat([send_idx[g][:send_owned[g]] for g in range(world)])] = back
+    h_local[src_owned] = back
     if return_stats:
         return h_local, dict(iterations=iterations, ghost_width=w, ghost_fraction=(pos_slab.shape[0] - n_owned) / max(n_owned, 1),
                              owned=n_owned, local_set=int(pos_slab.shape[0]))

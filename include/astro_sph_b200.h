@@ -249,6 +249,28 @@ int ast_table_interp(const ast_table_params *t, const double *const *x_cols /* h
                      const int64_t *x_strides /* host, in elements */, int64_t n, const double *base /* nullable */,
                      double *out, void *stream);
 
+/* ---- multi-GPU k-NN exchange (slabs along x + ghost zones): packing of the send buffer.  Rank g owns
+ * x in [bounds[g], bounds[g+1]); `owner[i]` is the owning rank of local particle i (decided on the bins of a global histogram so
+ * that every rank derives the same owner); a particle also goes, as a ghost, to every other rank whose slab lies within `w`
+ * of it (distance along the circle of circumference `length` from bounds[0] when `periodic`; every rank when `covers_all`).
+ * ast_slab_route_count fills counts[0..world) = owned rows per destination and counts[world..2 world) = ghost rows per
+ * destination (device, int64) and leaves the scanned block table in the workspace; ast_slab_route_write (same params, same
+ * workspace, after the count) writes the send buffer  [owned -> 0 | owned -> 1 | ... | ghosts -> 0 | ghosts -> 1 | ...]
+ * (rows of 3 doubles, ascending particle index inside each piece) and src_index[row] = local particle index.
+ * The per-rank particle split is the reference's io/EAGLE/_SnapshotEAGLE.py:120-130; the search itself is ast_knn_h. */
+#define AST_ROUTE_MAX_WORLD 32
+typedef struct ast_slab_route_params {
+    int64_t n;
+    int32_t world, periodic, covers_all, reserved;
+    double length, w;
+    double bounds[AST_ROUTE_MAX_WORLD + 1];
+} ast_slab_route_params;
+int ast_slab_route_workspace_bytes(const ast_slab_route_params *p, size_t *bytes);
+int ast_slab_route_count(const ast_slab_route_params *p, const double *pos, const int64_t *owner, int64_t *counts,
+                         void *workspace, size_t workspace_bytes, void *stream);
+int ast_slab_route_write(const ast_slab_route_params *p, const double *pos, const int64_t *owner, double *send,
+                         int64_t *src_index, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- misc ---- */
 const char *ast_last_error(void);
 int ast_abi_version(void);

@@ -172,3 +172,31 @@ def test_spatial_pre_ordering_gives_the_same_map(oracle):
     assert g.last_stats["reordered"] is False
     for m in (a3, b3):
         assert rel_l2(m, ref3) <= 1e-5 and abs(m.sum() - ref3.sum()) <= 1e-6 * np.abs(ref3).sum()
+
+
+@pytest.mark.parametrize("periodic,world,wfrac", [(True, 4, 0.03), (True, 8, 0.2), (False, 3, 0.05), (True, 2, 0.6), (False, 5, 0.0)])
+def test_slab_packing_kernel_equals_the_torch_route(periodic, world, wfrac):
+    """ast_slab_route_count / _write (the exchange step of the multi-GPU k-NN) against the torch index-op definition of the same
+    routing (distributed._route_torch, which the gloo tests run on the CPU): identical counts, send rows and source indices,
+    for wrapped ghost zones, ghost zones wider than a slab, no ghost zone, and a width that covers the whole box"""
+    import torch
+    from astro_sph_tools_b200 import distributed as astd
+    rng = np.random.default_rng(world * 7 + int(periodic))
+    n = 70001
+    length, lo = 2.5, (0.0 if periodic else -1.0)
+    pos = rng.uniform(lo, lo + length, (n, 3))
+    pos[:, 0] = lo + length * rng.beta(0.7, 1.3, n)                     # uneven along x: slabs of unequal width
+    pos_d = torch.from_numpy(pos).cuda()
+    x = pos_d[:, 0].contiguous()
+    edges = np.sort(rng.choice(np.arange(1, 4096), world - 1, replace=False))
+    bounds = torch.from_numpy(lo + length * np.concatenate([[0], edges, [4096]]) / 4096.0).cuda()
+    bins = torch.clamp(((x - lo) / length * 4096).floor().long(), 0, 4095)
+    owner = torch.bucketize(bins, torch.from_numpy(edges).cuda(), right=True)
+    w = wfrac * length
+    covers_all = periodic and w >= 0.5 * length
+    ref_send, ref_src, ref_counts = astd._route_torch(pos_d, x, owner, bounds[:-1], bounds[1:], w, length, periodic, covers_all, world)
+    send, src, counts = astd._SlabRouter(pos_d.device).route(pos_d, owner, bounds, w, length, periodic, covers_all, world)
+    torch.cuda.synchronize()
+    assert torch.equal(counts, ref_counts)
+    assert torch.equal(src, ref_src) and torch.equal(send, ref_send)
+    assert int(counts[0].sum()) == n                                     # every particle is owned exactly once
