@@ -680,12 +680,9 @@ static int launch_select(const ast_knn_params *p, const KnnLayout &L, KnnArgs &a
     const int nbk = (L.G + kSelBS - 1) / kSelBS;
     const unsigned nblocks = (unsigned)nbk * nbk * nbk;
     const size_t smem = sizeof(SelShared);
-    static bool attr_set = false;
-    if (!attr_set) {
-        AST_CUDA_TRY(cudaFuncSetAttribute(knn_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AST_CUDA_TRY(cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // (set on every call: the attribute belongs to the current device, and a process may drive several)
+    AST_CUDA_TRY(cudaFuncSetAttribute(knn_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AST_CUDA_TRY(cudaFuncSetAttribute(knn_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.g.box > 0.0) knn_select_kernel<true><<<nblocks, kSelThreads, smem, s>>>(a, sp);
     else knn_select_kernel<false><<<nblocks, kSelThreads, smem, s>>>(a, sp);
     AST_KERNEL_CHECK(s, "knn_select_kernel");
@@ -700,7 +697,8 @@ static int launch_select(const ast_knn_params *p, const KnnLayout &L, KnnArgs &a
         a.qlist = L.qlist;
         a.nq = (int64_t)n_fail;
     }
-    if (getenv("AST_KNN_VERBOSE")) fprintf(stderr, "[ast_knn_h] selection kernel: %u of %lld queries left to the lock-step kernel\n", n_fail, (long long)a.nq);
+    static const bool verbose = env_flag("AST_KNN_VERBOSE", false);
+    if (verbose) fprintf(stderr, "[ast_knn_h] selection kernel: %u queries left to the lock-step kernel\n", n_fail);
     return AST_OK;
 }
 
