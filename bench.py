@@ -657,8 +657,8 @@ def main():
     if fp32["updates_per_s"]:
         fp32["useful_issue_frac_at_max_clock"] = fp32["updates_per_s"] * 9.6 / fp32["issue_peak_lane_instr_per_s"]
         fp32["useful_mufu_frac_at_max_clock"] = fp32["updates_per_s"] / fp32["mufu_peak_sqrt_per_s"]
-    fp32["ncu"] = {"source": "profiles/r02_v3_ncu_summary.txt (rowcol_accum_kernel<cubic,1>, config 3, one launch)", "issue_active": 0.818,
-                   "xu_pipe": 0.704, "fma_pipe": 0.553, "thread_instr_per_useful_update": 13.2, "evaluated_pixels_inside_support": 0.69}
+    fp32["ncu"] = {"source": "profiles/r02_v13_ncu_accum.txt (rowcol_accum_kernel<cubic,1>, config 3, one launch, final build of round 2)", "issue_active": 0.826,
+                   "xu_pipe": 0.713, "fma_pipe": 0.551, "thread_instr_per_useful_update": 13.2, "evaluated_pixels_inside_support": 0.69}
 
     # ---- end to end through the public host-buffer API (pinned host arrays in, numpy map out on rank 0)
     e2e = None
