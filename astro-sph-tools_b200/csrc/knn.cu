@@ -654,6 +654,12 @@ static bool select_usable(const ast_knn_params *p, const KnnLayout &L, bool want
     static const bool enabled = env_flag("AST_KNN_SELECT", true);
     if (!enabled || want_lists || (p->flags & (AST_KNN_DIVERGING | AST_KNN_NO_SELECT))) return false;
     if (L.G < 2 * (kSelBS + 2 * kSelR) || n_build < 4096) return false;        // wrapped region pieces must stay disjoint / minimum image
+    // the K-th neighbour has to lie within R = 2 cells (+ the query's offset in its cell) for the answer to be verifiable: with m
+    // particles per occupied cell it sits at (K / (4.19 m))^(1/3) cells.  Beyond ~2.1 nearly every query would fall through to
+    // the lock-step kernel after a wasted sweep (K > 77 at the default 2 per cell); a caller's cell_target below 2 is the slab
+    // decomposition's "2 per occupied cell", above 2 a true density (whose regions then exceed the staging buffer anyway)
+    const double m_occ = p->cell_target > 2.0 ? p->cell_target : 2.0;
+    if (cbrt((double)p->k / (4.19 * m_occ)) > 2.1) return false;
     if (!(p->box > 0.0)) {
         double lo = INFINITY, hi = 0.0;
         for (int c = 0; c < 3; ++c) { const double e = p->hi[c] - p->lo[c]; if (!(e > 0.0)) return false; lo = e < lo ? e : lo; hi = e > hi ? e : hi; }

@@ -173,7 +173,8 @@ def test_reach_limited_build_for_query_subsets(oracle, box):
 
 @pytest.mark.parametrize("kind,n,k,box", [("s1", 40, 48, 1.0), ("s1", 33, 48, None), ("uniform", 60000, 48, 1.0), ("uniform", 50000, 32, None),
                                           ("uniform", 50000, 100, 1.0), ("s2", 60000, 48, 1.0), ("s2", 60000, 16, None),
-                                          ("aniso", 50000, 48, None), ("dup", 40000, 48, 1.0)])
+                                          ("aniso", 50000, 48, None), ("dup", 40000, 48, 1.0), ("uniform", 60000, 1, 1.0), ("uniform", 60000, 2, None),
+                                          ("s1", 36, 64, 1.0), ("s1", 36, 77, 1.0), ("uniform", 300000, 48, 1.0)])
 def test_selection_kernel_bit_equal_to_scipy(oracle, kind, n, k, box):
     """the selection kernel (float32 histogram + exact float64 edge band, knn_select.cuh) with its lock-step remainder against
     scipy on jittered lattices, uniform, clustered (most queries fall back), anisotropic extents (1.4 : 1 : 1, still on the
