@@ -150,7 +150,8 @@ __global__ void knn_unsafe_kernel(const double *__restrict__ h, int64_t nq, doub
 __global__ void knn_gather_kernel(const double *__restrict__ pos, const uint64_t *__restrict__ sorted, int64_t n,
                                   double *__restrict__ xs, double *__restrict__ ys, double *__restrict__ zs,
                                   uint32_t *__restrict__ sidx, uint32_t *__restrict__ cbeg,
-                                  int64_t q_begin, int64_t q_end, uint32_t *__restrict__ qflag)
+                                  int64_t q_begin, int64_t q_end, uint32_t *__restrict__ qflag, const uint32_t *__restrict__ orig_flag,
+                                  uint32_t flag_value)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -163,16 +164,16 @@ __global__ void knn_gather_kernel(const double *__restrict__ pos, const uint64_t
     // per-cell counts from the run boundaries of the sorted keys (cbeg pre-zeroed): count = end - begin
     if (s == n - 1 || (uint32_t)(sorted[s + 1] >> 32) != key) atomicAdd(&cbeg[key], (uint32_t)(s + 1));
     if (s == 0 || (uint32_t)(sorted[s - 1] >> 32) != key) atomicSub(&cbeg[key], (uint32_t)s);
-    if (qflag) qflag[s] = ((int64_t)i >= q_begin && (int64_t)i < q_end) ? 1u : 0u;
+    if (qflag) qflag[s] = orig_flag ? (orig_flag[i] == flag_value ? 1u : 0u) : (((int64_t)i >= q_begin && (int64_t)i < q_end) ? 1u : 0u);
 }
 
 __global__ void knn_compact_kernel(const uint32_t *__restrict__ qexcl, const uint32_t *__restrict__ sidx, int64_t n, int64_t q_begin,
-                                   int64_t q_end, uint32_t *__restrict__ qlist)
+                                   int64_t q_end, uint32_t *__restrict__ qlist, const uint32_t *__restrict__ orig_flag, uint32_t flag_value)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int64_t i = sidx[s];
-    if (i >= q_begin && i < q_end) qlist[qexcl[s]] = (uint32_t)s;
+    if (orig_flag ? orig_flag[i] == flag_value : (i >= q_begin && i < q_end)) qlist[qexcl[s]] = (uint32_t)s;
 }
 
 // max-heap on (d2, idx): root = current K-th smallest.  The heap is a per-thread (local-memory) array on purpose: a
@@ -531,7 +532,40 @@ __global__ void knn_fail_compact_kernel(const uint32_t *__restrict__ excl, int64
     if (nx != e) qlist[e] = (uint32_t)s;
 }
 
+// Pending queries leave for another grid when this one does not suit their surroundings (multi-level search).  On a grid sized
+// for the mean density a query inside a halo looks at thousands of candidates per cell of its 27-cell neighbourhood (NFW-clustered
+// 256^3: a third of the queries made 88 % of all candidate evaluations), and a query in a void walks four or five rings of
+// near-empty cells.  n27 = particles in the 3^3 cells around the query's own cell (clipped at the grid faces, no wrap: it is a
+// cost estimate, not part of the result): n27 >= thr_hi -> level[particle] = 1 (fine grid), n27 < thr_lo -> 2 (coarse grid).
+__global__ void knn_level_split_kernel(uint32_t *__restrict__ qflag, const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ cstart,
+                                       const uint32_t *__restrict__ sidx, int64_t n, int G, uint32_t thr_hi, uint32_t thr_lo,
+                                       uint32_t *__restrict__ level, unsigned long long *__restrict__ count)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t lv = 0;
+    if (s < n && qflag[s]) {
+        const uint32_t key = (uint32_t)(sorted[s] >> 32);
+        const int cz = (int)(key % (uint32_t)G), cy = (int)((key / (uint32_t)G) % (uint32_t)G), cx = (int)(key / ((uint32_t)G * (uint32_t)G));
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G - 1);
+        uint32_t n27 = 0;
+        for (int x = max(cx - 1, 0); x <= min(cx + 1, G - 1); ++x)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, G - 1); ++y) {
+                const uint32_t base = ((uint32_t)x * G + y) * G;
+                n27 += cstart[base + z1 + 1] - cstart[base + z0];
+            }
+        lv = n27 >= thr_hi ? 1u : (n27 < thr_lo ? 2u : 0u);
+        if (lv) { qflag[s] = 0u; level[sidx[s]] = lv; }
+    }
+    const unsigned b1 = __ballot_sync(0xffffffffu, lv == 1u), b2 = __ballot_sync(0xffffffffu, lv == 2u);
+    if ((threadIdx.x & 31) == 0) {
+        if (b1) atomicAdd(count, (unsigned long long)__popc(b1));
+        if (b2) atomicAdd(count + 1, (unsigned long long)__popc(b2));
+    }
+}
+
 struct KnnLayout {
+    int G2, G0;                                                    // fine / coarse grid of the multi-level search (0: none)
+    uint32_t *dense;                                               // per particle index: 1 = the query moved to the fine grid, 2 = to the coarse one
     int G;
     int64_t ncell, nq;
     uint64_t *ea, *eb;
@@ -564,6 +598,12 @@ static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
     double g = floor(cbrt((double)(p->n > 0 ? p->n : 1) / m));
     L.G = g < 1 ? 1 : (g > 1000 ? 1000 : (int)g);
     L.ncell = (int64_t)L.G * L.G * L.G;
+    // fine grid for the queries in dense surroundings: cells up to 4 times smaller per axis, at most 1000^3 of them
+    static const int fine_max = env_int("AST_KNN_FINE_FACTOR", 4);
+    const int fine = L.G >= 16 ? (fine_max * L.G <= 1000 ? fine_max : 1000 / L.G) : 0;
+    L.G2 = fine >= 2 ? fine * L.G : 0;
+    L.G0 = L.G >= 16 ? L.G / 2 : 0;
+    const int64_t ncell_max = L.G2 ? (int64_t)L.G2 * L.G2 * L.G2 : L.ncell;
     const int64_t n = p->n > 0 ? p->n : 1;
     L.nq = p->q_count > 0 ? p->q_count : p->n;
     Carver c(ws);
@@ -573,14 +613,15 @@ static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
     L.ys = c.take<double>(n);
     L.zs = c.take<double>(n);
     L.sidx = c.take<uint32_t>(n);
-    L.cbeg = c.take<uint32_t>(L.ncell + 1);
-    L.cell_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(L.ncell + 1));
+    L.cbeg = c.take<uint32_t>(ncell_max + 1);
+    L.cell_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(ncell_max + 1));
+    L.dense = c.take<uint32_t>(n);
     L.qflag = c.take<uint32_t>(n);
     L.qlist = c.take<uint32_t>(n);
     L.scan_tmp = (uint32_t *)c.take<char>(scan_workspace_bytes<uint32_t>(n));
     L.kept = c.take<uint32_t>(n);
     L.bbox_part = c.take<double>(256 * 6);
-    L.counter = c.take<unsigned long long>(4);
+    L.counter = c.take<unsigned long long>(6);
     L.sort_ws = c.take<char>(sort_workspace_bytes(n));
     L.bytes = c.bytes();
     return L;
@@ -611,7 +652,8 @@ static void launch_lockstep(const KnnArgs &a, bool want_idx, cudaStream_t s)
 // builds the cell list of `pos` in the workspace (steps 1 and 2) and fills the grid / array part of KnnArgs
 // (kept != nullptr: from the n_build particles listed there only)
 static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout &L, bool subset, int64_t q_begin, int64_t q_end,
-                     cudaStream_t s, KnnArgs &a, int64_t n_build = -1, const uint32_t *kept = nullptr)
+                     cudaStream_t s, KnnArgs &a, int64_t n_build = -1, const uint32_t *kept = nullptr, const uint32_t *orig_flag = nullptr,
+                     const uint64_t **sorted_out = nullptr, uint32_t flag_value = 1u)
 {
     KnnGrid g;
     g.G = L.G;
@@ -633,12 +675,13 @@ static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout
     const uint64_t *sorted = in_b ? L.eb : L.ea;
     AST_CUDA_TRY(cudaMemsetAsync(L.cbeg, 0, sizeof(uint32_t) * (L.ncell + 1), s));
     knn_gather_kernel<<<nb, 256, 0, s>>>(pos, sorted, n, L.xs, L.ys, L.zs, L.sidx, L.cbeg, q_begin, q_end,
-                                         subset ? L.qflag : nullptr);
+                                         subset ? L.qflag : nullptr, orig_flag, flag_value);
     AST_CUDA_TRY(scan_exclusive<uint32_t>(L.cbeg, L.ncell + 1, L.cell_tmp, nullptr, s));      // counts -> cstart
     if (subset) {
         AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n, L.scan_tmp, nullptr, s));
-        knn_compact_kernel<<<nb, 256, 0, s>>>(L.qflag, L.sidx, n, q_begin, q_end, L.qlist);
+        knn_compact_kernel<<<nb, 256, 0, s>>>(L.qflag, L.sidx, n, q_begin, q_end, L.qlist, orig_flag, flag_value);
     }
+    if (sorted_out) *sorted_out = sorted;
     a.g = g;
     a.xs = L.xs; a.ys = L.ys; a.zs = L.zs; a.sidx = L.sidx; a.cstart = L.cbeg;
     a.qlist = subset ? L.qlist : nullptr;
@@ -669,7 +712,8 @@ static bool select_usable(const ast_knn_params *p, const KnnLayout &L, bool want
 }
 
 // runs the selection kernel for every query; *need_lockstep = some queries were flagged (a.qlist / a.nq then describe them)
-static int launch_select(const ast_knn_params *p, const KnnLayout &L, KnnArgs &a, int64_t n_build, cudaStream_t s, bool *need_lockstep)
+static int launch_select(const ast_knn_params *p, const KnnLayout &L, KnnArgs &a, int64_t n_build, const uint64_t *sorted, cudaStream_t s,
+                         bool *need_lockstep, int64_t *n_dense, int64_t *n_sparse)
 {
     SelParams sp;
     double cs_min = a.g.cs[0] < a.g.cs[1] ? a.g.cs[0] : a.g.cs[1];
@@ -693,10 +737,28 @@ static int launch_select(const ast_knn_params *p, const KnnLayout &L, KnnArgs &a
     else knn_select_kernel<false><<<nblocks, kSelThreads, smem, s>>>(a, sp);
     AST_KERNEL_CHECK(s, "knn_select_kernel");
     uint32_t n_fail = 0;
+    unsigned long long moved[2] = { 0, 0 };
     uint32_t *total = reinterpret_cast<uint32_t *>(L.counter + 2);
+    // measured on the NFW-clustered 256^3 set (ms per call): one level 103.4; fine grid for n27 >= 60: 96.3, 100: 86.6, 200: 78.7,
+    // 400: 76.5, 1000: 76.7 (cells 2 / 3 / 4 times smaller: 79.0 / 74.7 / 77.2).  A COARSE grid (cells twice as large) for the queries
+    // of near-empty surroundings loses: n27 < 20: 88.4, 40: 87.7, 150: 93.7 -- walking rings of empty cells is cheaper than the
+    // eightfold candidates of every occupied one; off unless AST_KNN_SPARSE_N27 is set.
+    static const int thr_hi = env_int("AST_KNN_DENSE_N27", 400), thr_lo = env_int("AST_KNN_SPARSE_N27", 0);
+    const bool multi = (L.G2 > 0 && thr_hi > 0) || (L.G0 > 0 && thr_lo > 0);
+    if (multi) {
+        AST_CUDA_TRY(cudaMemsetAsync(L.dense, 0, sizeof(uint32_t) * (size_t)(p->n > 0 ? p->n : 1), s));
+        AST_CUDA_TRY(cudaMemsetAsync(L.counter + 3, 0, 2 * sizeof(unsigned long long), s));
+        knn_level_split_kernel<<<(unsigned)((n_build + 255) / 256), 256, 0, s>>>(L.qflag, sorted, a.cstart, a.sidx, n_build, L.G,
+                                                                                 L.G2 > 0 && thr_hi > 0 ? (uint32_t)thr_hi : 0xffffffffu,
+                                                                                 L.G0 > 0 && thr_lo > 0 ? (uint32_t)thr_lo : 0u, L.dense, L.counter + 3);
+        AST_KERNEL_CHECK(s, "knn_level_split_kernel");
+    }
     AST_CUDA_TRY(scan_exclusive<uint32_t>(L.qflag, n_build, L.scan_tmp, total, s));
     AST_CUDA_TRY(cudaMemcpyAsync(&n_fail, total, sizeof n_fail, cudaMemcpyDeviceToHost, s));
+    if (multi) AST_CUDA_TRY(cudaMemcpyAsync(moved, L.counter + 3, sizeof moved, cudaMemcpyDeviceToHost, s));
     AST_CUDA_TRY(cudaStreamSynchronize(s));
+    *n_dense = (int64_t)moved[0];
+    *n_sparse = (int64_t)moved[1];
     *need_lockstep = n_fail > 0;
     if (n_fail) {
         knn_fail_compact_kernel<<<(unsigned)((n_build + 255) / 256), 256, 0, s>>>(L.qflag, n_build, total, L.qlist);
@@ -704,7 +766,7 @@ static int launch_select(const ast_knn_params *p, const KnnLayout &L, KnnArgs &a
         a.nq = (int64_t)n_fail;
     }
     static const bool verbose = env_flag("AST_KNN_VERBOSE", false);
-    if (verbose) fprintf(stderr, "[ast_knn_h] selection kernel: %u queries left to the lock-step kernel\n", n_fail);
+    if (verbose) fprintf(stderr, "[ast_knn_h] selection kernel: %u queries left to the lock-step kernel on this grid (G = %d), %llu to the fine grid (G = %d), %llu to the coarse grid (G = %d)\n", n_fail, L.G, moved[0], L.G2, moved[1], L.G0);
     return AST_OK;
 }
 
@@ -808,7 +870,8 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
         KnnArgs a;
         const int64_t n_fast = limited ? n_build : n;
         const bool fast = select_usable(p, L, want, n_fast);
-        rc = knn_build(p, pos, L, subset && !fast, q_begin, q_end, s, a, limited ? n_build : -1, limited ? L.kept : nullptr);
+        const uint64_t *sorted = nullptr;
+        rc = knn_build(p, pos, L, subset && !fast, q_begin, q_end, s, a, limited ? n_build : -1, limited ? L.kept : nullptr, nullptr, &sorted);
         if (rc) return rc;
         a.nq = nq;
         a.q_begin = q_begin;
@@ -820,9 +883,11 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
             else launch_query<128>(a, want, s);
         } else {
             bool run_lockstep = true;
+            int64_t n_moved[2] = { 0, 0 };
             if (fast) {
-                // selection kernel over blocks of cells (knn_select.cuh); what it cannot verify goes to the lock-step kernel
-                rc = launch_select(p, L, a, n_fast, s, &run_lockstep);
+                // selection kernel over blocks of cells (knn_select.cuh); what it cannot verify goes to the lock-step kernel,
+                // on this grid or -- queries in dense / near-empty surroundings -- on a finer / coarser one
+                rc = launch_select(p, L, a, n_fast, sorted, s, &run_lockstep, &n_moved[0], &n_moved[1]);
                 if (rc) return rc;
             }
             if (run_lockstep) {
@@ -830,6 +895,25 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
                 else if (p->k <= 48) launch_lockstep<48>(a, want, s);
                 else if (p->k <= 64) launch_lockstep<64>(a, want, s);
                 else launch_lockstep<128>(a, want, s);
+            }
+            for (int lv = 0; lv < 2; ++lv) {
+                if (n_moved[lv] <= 0) continue;
+                // another level: the same particles on cells L.G2 / L.G times smaller (lv 0) or twice as large (lv 1); the buffers
+                // of the previous level are free again once its kernels have run (same stream); queries = particles flagged lv + 1
+                KnnLayout Lx = L;
+                Lx.G = lv == 0 ? L.G2 : L.G0;
+                Lx.ncell = (int64_t)Lx.G * Lx.G * Lx.G;
+                KnnArgs ax;
+                rc = knn_build(p, pos, Lx, true, q_begin, q_end, s, ax, limited ? n_build : -1, limited ? L.kept : nullptr, L.dense, nullptr,
+                               (uint32_t)(lv + 1));
+                if (rc) return rc;
+                ax.nq = n_moved[lv];
+                ax.q_begin = q_begin;
+                ax.h_out = h_out; ax.idx_out = idx_out; ax.dist_out = dist_out;
+                if (p->k <= 32) launch_lockstep<32>(ax, want, s);
+                else if (p->k <= 48) launch_lockstep<48>(ax, want, s);
+                else if (p->k <= 64) launch_lockstep<64>(ax, want, s);
+                else launch_lockstep<128>(ax, want, s);
             }
         }
         AST_CUDA_TRY(cudaGetLastError());
