@@ -401,6 +401,21 @@ def sub_c2(ctx, args, peak):
            "ms": ms, "particles_per_s": N / (ms * 1e-3), "stage_ms": stage, "pairs": eng.last_stats["n_pairs"],
            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
                         "algorithmic_bytes": alg}}
+    # the same particles in a fixed random order (the cost of an incoherent input order; presort="auto" looks at a
+    # sample of the order and projects a tile-ordered copy, "never" runs on the order as given)
+    perm = torch.randperm(N, device=ctx.dev, generator=torch.Generator(device=ctx.dev).manual_seed(1))
+    pos_r, h_r, props_r = pos_d[perm].contiguous(), h_d[perm].contiguous(), [q[perm].contiguous() for q in props_d]
+    out_r = torch.empty_like(out)
+    ro = {}
+    for mode in ("auto", "never"):
+        fr = lambda: eng.project(pos_r, h_r, props_r, size, CoordinateAxes.Z, bounds, "cubic_spline_3d", out=out_r, presort=mode)
+        ro[mode] = timed_device(ctx, fr, 3, 2)
+        if mode == "auto":
+            ro["reordered"] = bool(eng.last_stats["reordered"])
+            ro["rel_l2_vs_lattice_order_map"] = float(((out_r - out).norm() / out.norm()).item())
+    rec["random_order"] = {"ms_presort_auto": ro["auto"], "ms_presort_never": ro["never"], "reordered": ro["reordered"],
+                           "rel_l2_vs_lattice_order_map": ro["rel_l2_vs_lattice_order_map"]}
+    del pos_r, h_r, props_r, out_r, perm
     # parity on a window of the timed maps
     wp = 128
     p0, lo, hi = window_bounds(npix, wp)
