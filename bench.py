@@ -561,7 +561,13 @@ def main():
     subs = {}
     want = [] if args.no_sub else [s for s in args.sub.split(",") if s]
     if "c5" in want:
-        subs["c5"] = sub_c5(ctx, args, pos_all_d, peak)
+        if world == 1:
+            try:
+                subs["c5"] = sub_c5(ctx, args, pos_all_d, peak)
+            except Exception as e:                                # a sub-record must not lose the headline line
+                subs["c5"] = {"error": f"{type(e).__name__}: {e}"}
+        else:                                                     # (collectives inside: every rank fails or none)
+            subs["c5"] = sub_c5(ctx, args, pos_all_d, peak)
     run_c5_full = ("c5full" in want) or ("c5" in want and world == 8)
     sol._ws = None
     pos_d = pos_all_d[lo_i:hi_i].clone() if world > 1 else pos_all_d
