@@ -295,12 +295,23 @@ struct Acc3 {
 // walks the brick's list on its own, 32 entries at a time: every lane stages one entry (float64 -> brick-relative float32),
 // tests it against the warp's column, hits are compacted into the warp's shared-memory slots with a ballot (entries whose
 // column lies wholly in the outer annulus q >= 1 of the cubic spline go to a second, cheaper loop), then every lane
-// evaluates the hits for its 4 voxels (contiguous in z).
+// evaluates the hits for its 4 voxels (contiguous in z).  For batches with enough hits the staging lane also writes the
+// entry's squared in-plane distances to the 16 (x, y) voxel columns and its squared z-distances to the 8 levels (in units of
+// h), as the 2-D kernel does with its rows and columns: an evaluating lane then fetches one in-plane value and four level
+// values (LDS.32 + LDS.128) and the squared radius of a voxel is one FADD instead of 11 instructions per entry and lane.
+constexpr int kBrickTabMinHits = 10;
+struct __align__(16) BrickSlot {
+    float4 axy[4];       // squared in-plane distance to voxel column (x = i, y = j) at [i].{x,y,z,w}[j]   -- or the classic view:
+                         // axy[0] = {ux*sx, uy*sy, uz*sz, c}, axy[1] = {sx, sy, sz, -}
+    float4 cz[2];        // squared z-distance to levels 0..3, 4..7
+    float4 w;            // {c, -, -, -}
+};
+static_assert(sizeof(BrickSlot) == 112, "slot layout");
+
 template <int SHAPE>
 __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
 {
-    __shared__ float4 sP[4][32];        // {ux*sx, uy*sy, uz*sz, c}
-    __shared__ float4 sS[4][32];        // {sx, sy, sz, -}
+    __shared__ BrickSlot sB[4][32];
     TileWork w;
     if (!resolve_work(a, w)) return;
     const int brick = w.tile;
@@ -317,6 +328,7 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
     const float zf0 = (float)zl, zf1 = (float)(zl + 1), zf2 = (float)(zl + 2), zf3 = (float)(zl + 3);
     const float lox = 4.f * (float)(warp >> 1), loy = 4.f * (float)(warp & 1);
     const float d0 = (float)a.d[0], d1 = (float)a.d[1], d2 = (float)a.d[2];
+    BrickSlot *const slots = sB[warp];
     float acc[4] = { 0.f, 0.f, 0.f, 0.f };
     double acc64[4] = { 0.0, 0.0, 0.0, 0.0 };
     int since_fold = 0;
@@ -344,41 +356,86 @@ __global__ void __launch_bounds__(kAcc3Threads) brick_accum_kernel(Acc3 a)
         }
         const unsigned ball_f = __ballot_sync(0xffffffffu, hit && !outer);
         const unsigned ball_o = __ballot_sync(0xffffffffu, outer);
-        if (hit) {
-            const unsigned lt = (1u << lane) - 1u;
-            const int dst = outer ? 31 - __popc(ball_o & lt) : __popc(ball_f & lt);
-            sP[warp][dst] = P;
-            sS[warp][dst] = S;
-        }
-        __syncwarp();
         const int nf = __popc(ball_f), no = __popc(ball_o);
-        for (int e = 0; e < nf; ++e) {
-            const float4 s = sS[warp][e];
-            const float4 q = sP[warp][e];
-            const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
-            const float axy = fmaf(by2, by2, ax * ax);
-            const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
-            acc[0] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c0, c0, axy), a.tab), acc[0]);
-            acc[1] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c1, c1, axy), a.tab), acc[1]);
-            acc[2] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c2, c2, axy), a.tab), acc[2]);
-            acc[3] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c3, c3, axy), a.tab), acc[3]);
-        }
-        if (SHAPE == SHAPE_CUBIC) {
-            for (int e = 32 - no; e < 32; ++e) {
-                const float4 s = sS[warp][e];
-                const float4 q = sP[warp][e];
-                const float cc = q.w;
+        if (nf + no == 0) continue;
+        const unsigned lt = (1u << lane) - 1u;
+        const int dst = outer ? 31 - __popc(ball_o & lt) : __popc(ball_f & lt);
+        if (nf + no >= kBrickTabMinHits) {
+            if (hit) {
+                BrickSlot *d = slots + dst;
+                float ax2[4], by2[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float tx = fmaf(-(lox + (float)i), S.x, P.x), ty = fmaf(-(loy + (float)i), S.y, P.y);
+                    ax2[i] = tx * tx; by2[i] = ty * ty;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d->axy[i] = make_float4(ax2[i] + by2[0], ax2[i] + by2[1], ax2[i] + by2[2], ax2[i] + by2[3]);
+                float cz[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float t = fmaf(-(float)i, S.z, P.z); cz[i] = t * t; }
+                d->cz[0] = make_float4(cz[0], cz[1], cz[2], cz[3]);
+                d->cz[1] = make_float4(cz[4], cz[5], cz[6], cz[7]);
+                d->w = make_float4(P.w, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            const int col = lane >> 1;                           // (x, y) voxel column of this lane inside the warp's 4 x 4: x = col >> 2, y = col & 3
+            for (int e = 0; e < nf; ++e) {
+                const float axy = reinterpret_cast<const float *>(slots[e].axy)[col];
+                const float4 c = slots[e].cz[lane & 1];
+                const float cc = slots[e].w.x;
+                acc[0] = fmaf(cc, shape_half_full<SHAPE>(axy + c.x, a.tab), acc[0]);
+                acc[1] = fmaf(cc, shape_half_full<SHAPE>(axy + c.y, a.tab), acc[1]);
+                acc[2] = fmaf(cc, shape_half_full<SHAPE>(axy + c.z, a.tab), acc[2]);
+                acc[3] = fmaf(cc, shape_half_full<SHAPE>(axy + c.w, a.tab), acc[3]);
+            }
+            if (SHAPE == SHAPE_CUBIC) {
+                for (int e = 32 - no; e < 32; ++e) {
+                    const float axy = reinterpret_cast<const float *>(slots[e].axy)[col];
+                    const float4 c = slots[e].cz[lane & 1];
+                    const float cc = slots[e].w.x;
+                    const float a0 = __saturatef(fmaf(fast_sqrt(axy + c.x), -0.5f, 1.0f)), a1 = __saturatef(fmaf(fast_sqrt(axy + c.y), -0.5f, 1.0f));
+                    const float a2 = __saturatef(fmaf(fast_sqrt(axy + c.z), -0.5f, 1.0f)), a3 = __saturatef(fmaf(fast_sqrt(axy + c.w), -0.5f, 1.0f));
+                    acc[0] = fmaf(cc, a0 * a0 * a0, acc[0]);
+                    acc[1] = fmaf(cc, a1 * a1 * a1, acc[1]);
+                    acc[2] = fmaf(cc, a2 * a2 * a2, acc[2]);
+                    acc[3] = fmaf(cc, a3 * a3 * a3, acc[3]);
+                }
+            }
+        } else {
+            if (hit) {
+                slots[dst].axy[0] = P;
+                slots[dst].axy[1] = S;
+            }
+            __syncwarp();
+            for (int e = 0; e < nf; ++e) {
+                const float4 s = slots[e].axy[1];
+                const float4 q = slots[e].axy[0];
                 const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
                 const float axy = fmaf(by2, by2, ax * ax);
                 const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
-                float a0 = __saturatef(fmaf(fast_sqrt(fmaf(c0, c0, axy)), -0.5f, 1.0f));
-                float a1 = __saturatef(fmaf(fast_sqrt(fmaf(c1, c1, axy)), -0.5f, 1.0f));
-                float a2 = __saturatef(fmaf(fast_sqrt(fmaf(c2, c2, axy)), -0.5f, 1.0f));
-                float a3 = __saturatef(fmaf(fast_sqrt(fmaf(c3, c3, axy)), -0.5f, 1.0f));
-                acc[0] = fmaf(cc, a0 * a0 * a0, acc[0]);
-                acc[1] = fmaf(cc, a1 * a1 * a1, acc[1]);
-                acc[2] = fmaf(cc, a2 * a2 * a2, acc[2]);
-                acc[3] = fmaf(cc, a3 * a3 * a3, acc[3]);
+                acc[0] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c0, c0, axy), a.tab), acc[0]);
+                acc[1] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c1, c1, axy), a.tab), acc[1]);
+                acc[2] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c2, c2, axy), a.tab), acc[2]);
+                acc[3] = fmaf(q.w, shape_half_full<SHAPE>(fmaf(c3, c3, axy), a.tab), acc[3]);
+            }
+            if (SHAPE == SHAPE_CUBIC) {
+                for (int e = 32 - no; e < 32; ++e) {
+                    const float4 s = slots[e].axy[1];
+                    const float4 q = slots[e].axy[0];
+                    const float cc = q.w;
+                    const float ax = fmaf(-xf, s.x, q.x), by2 = fmaf(-yf, s.y, q.y);
+                    const float axy = fmaf(by2, by2, ax * ax);
+                    const float c0 = fmaf(-zf0, s.z, q.z), c1 = fmaf(-zf1, s.z, q.z), c2 = fmaf(-zf2, s.z, q.z), c3 = fmaf(-zf3, s.z, q.z);
+                    float a0 = __saturatef(fmaf(fast_sqrt(fmaf(c0, c0, axy)), -0.5f, 1.0f));
+                    float a1 = __saturatef(fmaf(fast_sqrt(fmaf(c1, c1, axy)), -0.5f, 1.0f));
+                    float a2 = __saturatef(fmaf(fast_sqrt(fmaf(c2, c2, axy)), -0.5f, 1.0f));
+                    float a3 = __saturatef(fmaf(fast_sqrt(fmaf(c3, c3, axy)), -0.5f, 1.0f));
+                    acc[0] = fmaf(cc, a0 * a0 * a0, acc[0]);
+                    acc[1] = fmaf(cc, a1 * a1 * a1, acc[1]);
+                    acc[2] = fmaf(cc, a2 * a2 * a2, acc[2]);
+                    acc[3] = fmaf(cc, a3 * a3 * a3, acc[3]);
+                }
             }
         }
         __syncwarp();
