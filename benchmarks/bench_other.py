@@ -4,6 +4,7 @@
   C4:       3-D voxel gridding of n^3 particles onto a (2n)^3 grid       -> particles/s
   C1:       64^3 -> 512^2 Wendland-C2 periodic surface density           -> particles/s
   ion:      HM01-shaped table lookup fused into ion weights (8(f) N3)    -> particles/s, GB/s; scipy timed beside it
+  halo:     nearest-halo lookup (8(f) N2): periodic 1-NN of the n^3 particles among 10^6 halo centres -> queries/s; scipy beside it
 Prints one JSON object per configuration."""
 import argparse
 import json
@@ -34,7 +35,7 @@ def timed(fn, reps=3, warm=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=256)
-    ap.add_argument("--which", default="knn,grid,c1,ion")
+    ap.add_argument("--which", default="knn,grid,c1,ion,halo")
     args = ap.parse_args()
     import torch
     from astro_sph_tools_b200 import synthetic, CoordinateAxes
@@ -85,6 +86,26 @@ def main():
         img = f()
         print(json.dumps({"config": "C1: S1 64^3 -> 512^2 Wendland C2 periodic surface density", "ms": ms, "particles_per_s": 64 ** 3 / (ms * 1e-3),
                           "mass_conservation_rel": abs(float(img.sum().item()) / 512 ** 2 - 1.0)}))
+    if "halo" in args.which:
+        # SURVEY 8(f) N2 (_scripts/find_nearest_haloes.py:207-215): KDTree(centres, boxsize=L).query(particle positions)
+        from scipy.spatial import cKDTree
+        n_halo = 1_000_000
+        centres = np.random.default_rng(9).uniform(0.0, 1.0, (n_halo, 3))
+        c_d = torch.from_numpy(centres).cuda()
+        f = lambda: sol.query(c_d, pos_d, 1, 1.0)
+        ms = timed(f, reps=3)
+        dist, idx = f()
+        sel = np.random.default_rng(2).choice(N, 200000, replace=False)
+        tree = cKDTree(centres, boxsize=1.0)
+        t0 = time.perf_counter(); d_ref, i_ref = tree.query(pos[sel], k=1, workers=1); t1 = time.perf_counter() - t0
+        t0 = time.perf_counter(); tree.query(pos[sel], k=1, workers=-1); ta = time.perf_counter() - t0
+        ok = bool(np.array_equal(dist.cpu().numpy()[sel, 0], d_ref) and np.array_equal(idx.cpu().numpy()[sel, 0], i_ref))
+        print(json.dumps({"config": f"nearest-halo lookup: periodic 1-NN of S1 {n}^3 = {N} particles among {n_halo} uniformly placed centres",
+                          "ms": ms, "queries_per_s": N / (ms * 1e-3), "bit_equal_to_scipy_on_sample": ok,
+                          "scipy_queries_per_s_1_core": len(sel) / t1, "scipy_queries_per_s_all_cores": len(sel) / ta, "cores": os.cpu_count(),
+                          "roofline": {"bound": "hbm", "algorithmic_bytes": N * (24 + 8 + 4) + n_halo * 24,
+                                       "frac": (N * 36 + n_halo * 24) / (ms * 1e-3) / 1e9 / peak}}), flush=True)
+        del c_d, dist, idx
     if "ion" in args.which:
         from astro_sph_tools_b200.tools.ionisation import IonisationTableBase
         r = np.random.default_rng(3)
