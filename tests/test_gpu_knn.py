@@ -198,3 +198,22 @@ def test_selection_kernel_bit_equal_to_scipy(oracle, kind, n, k, box):
     assert np.array_equal(got, ref)
     lo, cnt = len(pos) // 3, len(pos) // 4                          # a query slice through the fast path
     assert np.array_equal(gpu_knn(pos, k, box, kernel="select", q_begin=lo, q_count=cnt, full_build=True), ref[lo:lo + cnt])
+
+
+def test_selection_kernel_gates_and_boundaries(oracle):
+    """inputs at the edges of what the selection path accepts: points exactly on the faces of an open box, a set barely above
+    the 4096-particle threshold, an extent ratio just inside and just outside the 1.5 limit, and a mix of a dense clump with a
+    sparse field (fine grid for the clump, lock-step for the voids, selection for the rest)"""
+    rng = np.random.default_rng(77)
+    pos = rng.uniform(0, 1, (40000, 3))
+    pos[:200] = np.round(pos[:200])                                     # on the corners / faces of [0, 1]^3
+    assert np.array_equal(gpu_knn(pos, 48, None), oracle.knn_scipy(pos, 48, None, workers=-1)[0])
+    small = rng.uniform(0, 1, (4100, 3))
+    assert np.array_equal(gpu_knn(small, 16, 1.0), oracle.knn_scipy(small, 16, 1.0, workers=-1)[0])
+    for ratio in (1.49, 1.51):
+        q = rng.uniform(0, 1, (50000, 3)) * np.array([ratio, 1.0, 1.0])
+        assert np.array_equal(gpu_knn(q, 32, None), oracle.knn_scipy(q, 32, None, workers=-1)[0]), ratio
+    mix = np.concatenate([rng.uniform(0, 1, (60000, 3)), 0.5 + 0.004 * rng.normal(size=(40000, 3))]) % 1.0
+    assert np.array_equal(gpu_knn(mix, 48, 1.0), oracle.knn_scipy(mix, 48, 1.0, workers=-1)[0])
+    lo, cnt = 55000, 20000                                             # a query slice across the clump, reach-limited build
+    assert np.array_equal(gpu_knn(mix, 48, 1.0, q_begin=lo, q_count=cnt), oracle.knn_scipy(mix, 48, 1.0, workers=-1)[0][lo:lo + cnt])

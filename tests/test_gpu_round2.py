@@ -200,3 +200,28 @@ def test_slab_packing_kernel_equals_the_torch_route(periodic, world, wfrac):
     assert torch.equal(counts, ref_counts)
     assert torch.equal(src, ref_src) and torch.equal(send, ref_send)
     assert int(counts[0].sum()) == n                                     # every particle is owned exactly once
+
+
+def test_slab_packing_kernel_edge_cases():
+    """no particles at all; 32 destination ranks (the limit); every particle owned by one rank"""
+    import torch
+    from astro_sph_tools_b200 import distributed as astd
+    dev = torch.device("cuda")
+    router = astd._SlabRouter(dev)
+    bounds = torch.linspace(0.0, 1.0, 5, dtype=torch.float64, device=dev)
+    send, src, counts = router.route(torch.empty((0, 3), dtype=torch.float64, device=dev), torch.empty(0, dtype=torch.int64, device=dev),
+                                     bounds, 0.1, 1.0, True, False, 4)
+    assert send.shape == (0, 3) and src.numel() == 0 and int(counts.sum()) == 0
+    rng = np.random.default_rng(3)
+    pos = torch.from_numpy(rng.uniform(0, 1, (5000, 3))).to(dev)
+    x = pos[:, 0].contiguous()
+    b32 = torch.linspace(0.0, 1.0, 33, dtype=torch.float64, device=dev)
+    owner = torch.clamp((x * 32).floor().long(), 0, 31)
+    ref = astd._route_torch(pos, x, owner, b32[:-1], b32[1:], 0.01, 1.0, True, False, 32)
+    got = router.route(pos, owner, b32, 0.01, 1.0, True, False, 32)
+    torch.cuda.synchronize()
+    assert torch.equal(got[2], ref[2]) and torch.equal(got[1], ref[1]) and torch.equal(got[0], ref[0])
+    one = torch.zeros(5000, dtype=torch.int64, device=dev)
+    b1 = torch.tensor([0.0, 1.0], dtype=torch.float64, device=dev)
+    send, src, counts = router.route(pos, one, b1, 0.3, 1.0, True, False, 1)
+    assert counts.tolist() == [[5000], [0]] and torch.equal(src, torch.arange(5000, device=dev)) and torch.equal(send, pos)
