@@ -302,6 +302,14 @@ __global__ void __launch_bounds__(kSelThreads) knn_select_kernel(KnnArgs a, SelP
                         mask &= mask - 1u;
                     }
                 }
+                for (; i + 4 <= end; i += 4) {                   // tail of the run: groups of four, then single candidates
+                    const float4 c0 = S.cand[i], c1 = S.cand[i + 1], c2 = S.cand[i + 2], c3 = S.cand[i + 3];
+                    unsigned mask = (in_band(c0) ? 1u : 0u) | (in_band(c1) ? 2u : 0u) | (in_band(c2) ? 4u : 0u) | (in_band(c3) ? 8u : 0u);
+                    while (mask) {
+                        remember(i + __ffs((int)mask) - 1);
+                        mask &= mask - 1u;
+                    }
+                }
                 for (; i < end; ++i)
                     if (in_band(S.cand[i])) remember(i);
             }

@@ -283,8 +283,9 @@ def smoothing_lengths_slabs(pos_local, k=32, box_size=None, group=None, solver=N
     # global extent (periodic: the box) and the mean K-th neighbour distance it implies
     ext = torch.empty(6, dtype=torch.float64, device=dev)
     if n_loc:
-        ext[:3] = pos_local.min(dim=0).values
-        ext[3:] = -pos_local.max(dim=0).values
+        mn, mx = torch.aminmax(pos_local, dim=0)                  # one pass over the positions
+        ext[:3] = mn
+        ext[3:] = -mx
     else:
         ext[:] = float("inf")
     dist.all_reduce(ext, op=dist.ReduceOp.MIN, group=group)

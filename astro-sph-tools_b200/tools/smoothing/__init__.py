@@ -42,13 +42,13 @@ class SmoothingLengthSolver:
         p.n = n; p.k = int(k); p.flags = {"select": 0, "lockstep": 8, "diverging": 1}[kernel] | (4 if full_build else 0)      # AST_KNN_* query-kernel selection (csrc/knn.cu): select = selection over blocks of cells + lock-step for what it cannot verify (h only; neighbour lists always take the lock-step kernel)
         p.box = float(box_size) if box_size else 0.0
         if p.box <= 0.0 and n > 0:
-            lo = pos.min(dim=0).values.cpu(); hi = pos.max(dim=0).values.cpu()
+            lo, hi = (t.cpu() for t in torch.aminmax(pos, dim=0))            # one pass, one read-back
             if not (torch.isfinite(lo).all() and torch.isfinite(hi).all()):
                 raise ValueError("positions must be finite")
             for c in range(3):
                 p.lo[c] = float(lo[c]); p.hi[c] = float(hi[c])
         elif n > 0:
-            mn, mx = float(pos.min()), float(pos.max())
+            mn, mx = (float(v) for v in torch.stack(torch.aminmax(pos)).cpu())     # one pass over the positions, one read-back
             if not (mn >= 0.0 and mx < p.box):
                 raise ValueError("periodic k-NN needs 0 <= x < box_size (scipy boxsize semantics)")
         # mean particles per cell if the set filled the whole box; a caller whose set fills a fraction f of it (a slab of a
