@@ -563,6 +563,34 @@ __global__ void knn_level_split_kernel(uint32_t *__restrict__ qflag, const uint6
     }
 }
 
+// Order a query list by the crowding of the queries' surroundings (one class per factor 4 of the 27-cell count), keeping the
+// cell order inside each class: the 32 queries of a lock-step warp then need rings and candidate counts of similar size (ncu on
+// the clustered set: 16 of 32 threads per instruction when warps mix sparse and crowded queries).  NFW-clustered 256^3: 76.5 ms
+// unordered, 72.9 with a class per factor 2, 71.6 per factor 4, 77.6 per factor sqrt(2) (finer classes scatter the warps).
+__global__ void knn_qorder_key_kernel(const uint32_t *__restrict__ qlist, int64_t nq, const double *__restrict__ xs, const double *__restrict__ ys,
+                                      const double *__restrict__ zs, KnnGrid g, const uint32_t *__restrict__ cstart, uint64_t *__restrict__ keys)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    const uint32_t s = qlist[t];
+    const int G = g.G;
+    const int cx = cell_coord(g, xs[s], 0), cy = cell_coord(g, ys[s], 1), cz = cell_coord(g, zs[s], 2);
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G - 1);
+    uint32_t n27 = 0;
+    for (int x = max(cx - 1, 0); x <= min(cx + 1, G - 1); ++x)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, G - 1); ++y) {
+            const uint32_t base = ((uint32_t)x * G + y) * G;
+            n27 += cstart[base + z1 + 1] - cstart[base + z0];
+        }
+    const uint32_t cls = (uint32_t)min((31 - __clz((int)(n27 | 1u))) / 2, 15);
+    keys[t] = ((uint64_t)cls << 32) | (uint64_t)s;
+}
+__global__ void knn_qorder_unpack_kernel(const uint64_t *__restrict__ keys, int64_t nq, uint32_t *__restrict__ qlist)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nq) qlist[t] = (uint32_t)keys[t];
+}
+
 struct KnnLayout {
     int G2, G0;                                                    // fine / coarse grid of the multi-level search (0: none)
     uint32_t *dense;                                               // per particle index: 1 = the query moved to the fine grid, 2 = to the coarse one
@@ -688,6 +716,20 @@ static int knn_build(const ast_knn_params *p, const double *pos, const KnnLayout
     a.qpos = nullptr;
     a.k = p->k;
     AST_CUDA_TRY(cudaGetLastError());
+    return AST_OK;
+}
+
+// sorts a.qlist (a.nq entries) by crowding class; L.ea / L.eb are free once the cell list is built
+static int order_queries(const KnnLayout &L, const KnnArgs &a, cudaStream_t s)
+{
+    static const bool on = env_flag("AST_KNN_QORDER", true);
+    if (!on || !a.qlist || a.nq < 4096) return AST_OK;
+    const unsigned nb = (unsigned)((a.nq + 255) / 256);
+    knn_qorder_key_kernel<<<nb, 256, 0, s>>>(a.qlist, a.nq, a.xs, a.ys, a.zs, a.g, a.cstart, L.ea);
+    int in_b = 0;
+    AST_CUDA_TRY(radix_sort_u64(L.ea, L.eb, a.nq, 32, 4, L.sort_ws, s, &in_b));
+    knn_qorder_unpack_kernel<<<nb, 256, 0, s>>>(in_b ? L.eb : L.ea, a.nq, const_cast<uint32_t *>(a.qlist));
+    AST_KERNEL_CHECK(s, "knn_qorder");
     return AST_OK;
 }
 
@@ -891,6 +933,7 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
                 if (rc) return rc;
             }
             if (run_lockstep) {
+                if (fast) { rc = order_queries(L, a, s); if (rc) return rc; }
                 if (p->k <= 32) launch_lockstep<32>(a, want, s);
                 else if (p->k <= 48) launch_lockstep<48>(a, want, s);
                 else if (p->k <= 64) launch_lockstep<64>(a, want, s);
@@ -910,6 +953,8 @@ extern "C" int ast_knn_h(const ast_knn_params *p, const double *pos, double *h_o
                 ax.nq = n_moved[lv];
                 ax.q_begin = q_begin;
                 ax.h_out = h_out; ax.idx_out = idx_out; ax.dist_out = dist_out;
+                rc = order_queries(Lx, ax, s);
+                if (rc) return rc;
                 if (p->k <= 32) launch_lockstep<32>(ax, want, s);
                 else if (p->k <= 48) launch_lockstep<48>(ax, want, s);
                 else if (p->k <= 64) launch_lockstep<64>(ax, want, s);
