@@ -621,8 +621,12 @@ static KnnLayout knn_layout(const ast_knn_params *p, void *ws)
 {
     KnnLayout L;
     // mean particles per cell; measured on B200 (benchmarks/knn_probe.py, k = 48, 256^3): 2 per cell is twice as fast as
-    // k/3 per cell (the explored cube of cells hugs the k-neighbour sphere more tightly; empty cells are cheap)
-    const double m = p->cell_target > 0 ? p->cell_target : 2.0;
+    // k/3 per cell for the ring traversal (the explored cube of cells hugs the k-neighbour sphere more tightly; empty cells are
+    // cheap).  The selection kernel stages the 8^3 cells around a block in a buffer of 1152 candidates: at 2.0 per cell a region
+    // holds ~1030, at 2.2 most regions overflow and fall back (benchmarks/knn_celltarget_probe.py, whole call at 256^3:
+    // 1.5: 14.4 ms, 1.6: 14.3, 1.75: 14.4 with 113 fallbacks, 1.9: 15.0, 2.0: 15.9, 2.2: 26.4, 2.5: 36.5).  1.75 keeps 28 % of
+    // head room for denser regions and sweeps an eighth fewer candidates.
+    const double m = p->cell_target > 0 ? p->cell_target : 1.75;
     double g = floor(cbrt((double)(p->n > 0 ? p->n : 1) / m));
     L.G = g < 1 ? 1 : (g > 1000 ? 1000 : (int)g);
     L.ncell = (int64_t)L.G * L.G * L.G;
@@ -741,9 +745,9 @@ static bool select_usable(const ast_knn_params *p, const KnnLayout &L, bool want
     if (L.G < 2 * (kSelBS + 2 * kSelR) || n_build < 4096) return false;        // wrapped region pieces must stay disjoint / minimum image
     // the K-th neighbour has to lie within R = 2 cells (+ the query's offset in its cell) for the answer to be verifiable: with m
     // particles per occupied cell it sits at (K / (4.19 m))^(1/3) cells.  Beyond ~2.1 nearly every query would fall through to
-    // the lock-step kernel after a wasted sweep (K > 77 at the default 2 per cell); a caller's cell_target below 2 is the slab
-    // decomposition's "2 per occupied cell", above 2 a true density (whose regions then exceed the staging buffer anyway)
-    const double m_occ = p->cell_target > 2.0 ? p->cell_target : 2.0;
+    // the lock-step kernel after a wasted sweep (K > 67 at the default 1.75 per cell); a caller's cell_target below that is the slab
+    // decomposition's "1.75 per occupied cell", above it a true density (whose regions then exceed the staging buffer anyway)
+    const double m_occ = p->cell_target > 1.75 ? p->cell_target : 1.75;
     if (cbrt((double)p->k / (4.19 * m_occ)) > 2.1) return false;
     if (!(p->box > 0.0)) {
         double lo = INFINITY, hi = 0.0;

@@ -331,12 +331,12 @@ def smoothing_lengths_slabs(pos_local, k=32, box_size=None, group=None, solver=N
         src_owned = src[:n_send_owned]
         del send
         if n_owned:
-            # the slab + ghosts fill only a fraction of the box the cell grid spans: size the cells for ~2 particles per OCCUPIED
+            # the slab + ghosts fill only a fraction of the box the cell grid spans: size the cells for ~1.75 particles per OCCUPIED
             # cell (with the default, 8 slabs would put 14 particles in every occupied cell and 2000 candidates in front of a query)
             # (an open box is gridded over the bounding box of the local set itself: nothing to correct there)
             fill = min(1.0, float((b_hi[rank] - b_lo[rank]).item() + 2.0 * w) / length) if box_size else 1.0
             h_owned = solver.solve(pos_slab, k, box_size, q_begin=0, q_count=n_owned if n_owned < pos_slab.shape[0] else 0,
-                                   cell_target=max(2.0 * fill, 0.02))
+                                   cell_target=max(1.75 * fill, 0.02))
         else:
             h_owned = torch.empty(0, dtype=pos_local.dtype, device=dev)
         # ---- step 4: every neighbour within h of an owned query at x lies in [b_lo - w, b_hi + w]

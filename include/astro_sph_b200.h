@@ -196,7 +196,7 @@ typedef struct ast_knn_params {
     int32_t flags;
     double box;                  /* > 0: periodic cube [0, box)^3 ; <= 0: open */
     double lo[3], hi[3];         /* extent of the positions (open box); ignored when periodic */
-    double cell_target;          /* mean particles per cell; <= 0 = default (2) */
+    double cell_target;          /* mean particles per cell; <= 0 = default (1.75) */
     int64_t q_begin, q_count;    /* queries = particles [q_begin, q_begin + q_count); q_count <= 0 = all.  Multi-GPU:
                                     every rank holds all positions and answers its own slice of the queries.
                                     h_out / idx_out / dist_out hold q_count rows, row = particle - q_begin. */
